@@ -1,0 +1,940 @@
+// fp_api.cu -- the C ABI of libferiphys_cuda.so (include/feriphys_cuda.h):
+// handle management, host-side threshold derivation, step orchestration.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+
+#include "fp_internal.h"
+#include "fp_shard.h"
+
+namespace fp {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local std::string t_error;
+
+void set_error(const std::string &msg) { t_error = msg; }
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    t_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" +
+              std::to_string(line) + ")";
+    return FP_ERR_CUDA;
+}
+
+// ---- host-side thresholds ----------------------------------------------------
+// Ordinals of non-negative floats are their bit patterns.
+static inline uint32_t f2u(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+static inline float u2f(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// smallest m2 >= 0 with pred(sqrtf(m2)) true, for a predicate monotone (false..true) in m2;
+// returns NaN when no finite-or-inf m2 satisfies it.
+template <class Pred>
+static float smallest_m2(Pred pred) {
+    const uint32_t inf = 0x7f800000u;
+    if (pred(sqrtf(0.0f))) return 0.0f;
+    if (!pred(sqrtf(u2f(inf)))) return NAN;
+    uint32_t lo = 0, hi = inf;  // pred(lo) false, pred(hi) true
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (pred(sqrtf(u2f(mid)))) hi = mid; else lo = mid;
+    }
+    return u2f(hi);
+}
+
+// largest c in [-1, 1] with acosf(c) > theta; -2 when none.  acosf here is the
+// platform libm -- the function Rust's f32::acos calls.
+static float acos_threshold(float theta) {
+    if (!(acosf(-1.0f) > theta)) return -2.0f;
+    if (acosf(1.0f) > theta) return 1.0f;
+    auto ord = [](float f) -> int64_t {
+        const uint32_t u = f2u(f);
+        return (u & 0x80000000u) ? -(int64_t)(u & 0x7fffffffu) : (int64_t)u;
+    };
+    auto unord = [](int64_t o) -> float {
+        return o < 0 ? u2f(0x80000000u | (uint32_t)(-o)) : u2f((uint32_t)o);
+    };
+    int64_t lo = ord(-1.0f), hi = ord(1.0f);
+    while (hi - lo > 1) {
+        const int64_t mid = lo + (hi - lo) / 2;
+        if (acosf(unord(mid)) > theta) lo = mid; else hi = mid;
+    }
+    return unord(lo);
+}
+
+void derive_params(const fp_config &c, DevParams &P) {
+    P.dt = c.dt;
+    P.f_c = c.centering_factor;
+    P.f_v = c.velocity_matching_factor;
+    P.neg_f_a = -1.0f * c.avoidance_factor;
+    P.thr = c.distance_weight_threshold;
+    P.fall = c.distance_weight_threshold_falloff;
+    const float thr = P.thr;
+    const float R = thr + P.fall;  // f32 sum, as boid.rs:155
+    // rejected  <=>  !(dist <= thr) && dist >= R
+    const float m2_ge_R = smallest_m2([R](float d) { return d >= R; });
+    const float m2_gt_thr = smallest_m2([thr](float d) { return !(d <= thr); });
+    P.m2_cut = (isnan(m2_ge_R) || isnan(m2_gt_thr)) ? NAN : std::max(m2_ge_R, m2_gt_thr);
+    // weight 1  <=>  dist <= thr  <=>  m2 <= m2_one
+    if (isnan(m2_gt_thr)) P.m2_one = INFINITY;           // every distance is <= thr
+    else if (m2_gt_thr == 0.0f) P.m2_one = -1.0f;        // none is
+    else P.m2_one = u2f(f2u(m2_gt_thr) - 1);             // predecessor
+    P.cstar = acos_threshold(c.max_sight_angle);
+    P.cstar_lead = acos_threshold(c.max_sight_angle_to_lead_boid);
+    P.steer_secs = c.time_to_start_steering_secs;
+    P.steer_nanos = c.time_to_start_steering_nanos;
+    P.steering_overrides = c.steering_overrides ? 1 : 0;
+}
+
+}  // namespace fp
+
+using namespace fp;
+
+// ---- handle -------------------------------------------------------------------
+struct fp_flock {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t n = 0;        // boids held by this handle (local rows when sharded)
+    uint32_t cap = 0;      // capacity of pos/vel
+    uint64_t n_global = 0;
+    uint32_t first_index = 0;
+    fp_config cfg{};
+    DevParams P{};
+    float4 *pos[2] = {nullptr, nullptr}, *vel[2] = {nullptr, nullptr};
+    int cur = 0;
+    bool permuted = false;
+    int method = FP_METHOD_AUTO, method_in_use = FP_METHOD_ALLPAIRS;
+    float *d_leads = nullptr, *d_attr = nullptr, *d_obs = nullptr, *d_lead_table = nullptr;
+    uint32_t n_leads = 0, n_attr = 0, n_obs = 0, table_rows = 0, table_leads = 0, table_cursor = 0;
+    unsigned *d_status = nullptr;
+    unsigned long long *d_census = nullptr;
+    float *d_bounds = nullptr;
+    // grid
+    GridDesc grid{};
+    bool grid_valid = false, domain_user = false;
+    float user_lo[3]{}, user_hi[3]{};
+    uint64_t steps_since_fit = 0;
+    GridWork work{};
+    // staging for host transfers
+    void *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timed = false;
+    Shard *shard = nullptr;  // multi-GPU state (fp_shard.cu)
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(T **p, size_t count) {
+    *p = nullptr;
+    if (!count) count = 1;
+    FP_CUDA(cudaMalloc((void **)p, count * sizeof(T)));
+    return FP_OK;
+}
+template <class T>
+void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+int ensure_stage(fp_flock *f, size_t bytes) {
+    if (bytes <= f->stage_bytes) return FP_OK;
+    if (f->d_stage) cudaFree(f->d_stage);
+    f->d_stage = nullptr;
+    f->stage_bytes = 0;
+    FP_CUDA(cudaMalloc(&f->d_stage, bytes));
+    f->stage_bytes = bytes;
+    return FP_OK;
+}
+
+int check(fp_flock *f) {
+    if (!f) {
+        set_error("null flock handle");
+        return FP_ERR_INVALID;
+    }
+    FP_CUDA(cudaSetDevice(f->device));
+    return FP_OK;
+}
+
+int upload_table(fp_flock *f, float **dst, const float *src, size_t floats) {
+    dev_free(*dst);
+    if (!floats) return FP_OK;
+    int rc = dev_alloc(dst, floats);
+    if (rc) return rc;
+    FP_CUDA(cudaMemcpyAsync(*dst, src, floats * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));  // caller's buffer is not retained
+    return FP_OK;
+}
+
+void refresh_tables(fp_flock *f) {
+    f->P.leads = f->d_leads;
+    f->P.n_leads = (int)f->n_leads;
+    f->P.attractors = f->d_attr;
+    f->P.n_attractors = (int)f->n_attr;
+    f->P.obstacles = f->d_obs;
+    f->P.n_obstacles = (int)f->n_obs;
+}
+
+float reach_of(const fp_config &c) {
+    const float thr = c.distance_weight_threshold;
+    const float R = thr + c.distance_weight_threshold_falloff;
+    return std::max(thr, R);
+}
+
+void free_grid_work(fp_flock *f) {
+    dev_free(f->work.keys[0]);
+    dev_free(f->work.keys[1]);
+    dev_free(f->work.vals[0]);
+    dev_free(f->work.vals[1]);
+    dev_free(f->work.cell_start);
+    dev_free(f->work.tile_hist);
+    dev_free(f->work.scan_tmp);
+    f->work = GridWork{};
+}
+
+// Fit the uniform grid to the current positions (or the user's domain).
+int fit_grid(fp_flock *f) {
+    const float reach = reach_of(f->cfg);
+    if (!(reach > 0.0f) || !std::isfinite(reach)) {
+        set_error("grid method needs a finite positive distance_weight_threshold + falloff");
+        return FP_ERR_UNSUPPORTED;
+    }
+    float lo[3], hi[3];
+    if (f->domain_user) {
+        memcpy(lo, f->user_lo, sizeof(lo));
+        memcpy(hi, f->user_hi, sizeof(hi));
+    } else {
+        int rc = launch_bounds(f->stream, f->pos[f->cur], f->n, f->d_bounds);
+        if (rc) return rc;
+        float b[6];
+        FP_CUDA(cudaMemcpyAsync(b, f->d_bounds, sizeof(b), cudaMemcpyDeviceToHost, f->stream));
+        FP_CUDA(cudaStreamSynchronize(f->stream));
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = b[a];
+            hi[a] = b[3 + a];
+            if (!(lo[a] <= hi[a])) lo[a] = hi[a] = 0.0f;
+        }
+        if (f->shard) shard_reduce_bounds(f->shard, f->stream, lo, hi);
+    }
+    // cell edge > reach by a margin that covers the f32 rounding of the cell coordinate
+    // (relative 2^-23 of a coordinate < 4096 cells) and of the distance itself.
+    double cell = (double)reach * (1.0 + 1.0 / 512.0);
+    GridDesc g{};
+    for (;;) {
+        uint64_t ncells = 1;
+        bool ok = true;
+        for (int a = 0; a < 3; ++a) {
+            const double ext = (double)hi[a] - (double)lo[a];
+            const double d = floor(ext / cell) + 1.0;
+            if (!(d <= 4096.0)) { ok = false; break; }
+            g.dim[a] = (int)d;
+            ncells *= (uint64_t)g.dim[a];
+        }
+        if (ok && ncells <= (1ull << 24)) {
+            g.ncells = (uint32_t)ncells;
+            break;
+        }
+        cell *= 1.25;
+    }
+    g.cell = (float)cell;
+    g.inv_cell = 1.0f / g.cell;
+    for (int a = 0; a < 3; ++a) g.origin[a] = lo[a];
+    uint32_t bits = 1;
+    while ((1ull << bits) < g.ncells) ++bits;
+    g.key_bits = bits;
+    f->grid = g;
+
+    // scratch
+    GridWork &w = f->work;
+    const uint32_t cap = f->shard ? shard_capacity(f->shard) : f->n;
+    const size_t ntiles = ((size_t)cap + 4095) / 4096 + 1;
+    const size_t hist = 256 * ntiles;
+    const size_t scan_n = std::max(hist, (size_t)g.ncells + 1);
+    const size_t scan_tmp = scan_n / 4096 + 2;
+    if (cap > w.cap) {
+        dev_free(w.keys[0]); dev_free(w.keys[1]); dev_free(w.vals[0]); dev_free(w.vals[1]);
+        int rc;
+        if ((rc = dev_alloc(&w.keys[0], cap)) || (rc = dev_alloc(&w.keys[1], cap)) ||
+            (rc = dev_alloc(&w.vals[0], cap)) || (rc = dev_alloc(&w.vals[1], cap)))
+            return rc;
+        w.cap = cap;
+    }
+    if (hist > w.tile_hist_elems) {
+        dev_free(w.tile_hist);
+        int rc = dev_alloc(&w.tile_hist, hist);
+        if (rc) return rc;
+        w.tile_hist_elems = hist;
+    }
+    if ((size_t)g.ncells + 1 > w.cell_cap) {
+        dev_free(w.cell_start);
+        int rc = dev_alloc(&w.cell_start, (size_t)g.ncells + 1);
+        if (rc) return rc;
+        w.cell_cap = (size_t)g.ncells + 1;
+    }
+    if (scan_tmp > w.scan_tmp_elems) {
+        dev_free(w.scan_tmp);
+        int rc = dev_alloc(&w.scan_tmp, scan_tmp);
+        if (rc) return rc;
+        w.scan_tmp_elems = scan_tmp;
+    }
+    f->grid_valid = true;
+    f->steps_since_fit = 0;
+    return FP_OK;
+}
+
+int resolve_method(fp_flock *f) {
+    int m = f->method;
+    if (m == FP_METHOD_AUTO) {
+        const float reach = reach_of(f->cfg);
+        const bool grid_ok = reach > 0.0f && std::isfinite(reach);
+        const uint64_t ng = f->shard ? f->n_global : f->n;
+        if (ng <= small_max_boids() && !f->shard) m = FP_METHOD_SMALL;
+        else if (ng >= 32768 && grid_ok) m = FP_METHOD_GRID;
+        else m = FP_METHOD_ALLPAIRS;
+    }
+    if (m == FP_METHOD_SMALL && (f->n > small_max_boids() || f->shard)) m = FP_METHOD_ALLPAIRS;
+    f->method_in_use = m;
+    return m;
+}
+
+// bring the state back to caller index order (all-pairs sums in that order)
+int ensure_caller_order(fp_flock *f) {
+    if (!f->permuted) return FP_OK;
+    int rc = launch_unpermute(f->stream, f->pos[f->cur], f->vel[f->cur], f->pos[f->cur ^ 1],
+                              f->vel[f->cur ^ 1], f->n, f->first_index);
+    if (rc) return rc;
+    f->cur ^= 1;
+    f->permuted = false;
+    return FP_OK;
+}
+
+// sort the current state by cell; result (sorted) in pos[cur^1], cell_start valid
+int grid_prepare(fp_flock *f) {
+    if (!f->grid_valid || (!f->domain_user && f->steps_since_fit >= 256)) {
+        int rc = fit_grid(f);
+        if (rc) return rc;
+    }
+    int rc = launch_grid_keys(f->stream, f->grid, f->pos[f->cur], f->n, f->work);
+    if (rc) return rc;
+    int buf = 0;
+    rc = launch_radix_sort(f->stream, f->work, f->n, f->grid.key_bits, &buf);
+    if (rc) return rc;
+    return launch_grid_reorder(f->stream, f->work.vals[buf], f->pos[f->cur], f->vel[f->cur],
+                               f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], f->n);
+}
+
+void select_leads(fp_flock *f) {
+    if (f->d_lead_table && f->table_rows) {
+        const uint32_t row = std::min(f->table_cursor, f->table_rows - 1);
+        f->P.leads = f->d_lead_table + (size_t)row * f->table_leads * 8;
+        f->P.n_leads = (int)f->table_leads;
+    } else {
+        f->P.leads = f->d_leads;
+        f->P.n_leads = (int)f->n_leads;
+    }
+}
+
+int run_tap(fp_flock *f, int tap, const TapOut &out) {
+    select_leads(f);
+    if (f->shard) return shard_tap(f->shard, f, tap, out);
+    const int m = resolve_method(f);
+    if (m == FP_METHOD_GRID) {
+        int rc = grid_prepare(f);
+        if (rc) return rc;
+        // the sorted copy becomes the state (same boids, new order)
+        f->cur ^= 1;
+        f->permuted = true;
+        return launch_grid_walk(f->stream, f->P, f->grid, tap, f->pos[f->cur], f->vel[f->cur],
+                                f->work.cell_start, f->n, nullptr, nullptr, f->d_status, out, nullptr);
+    }
+    int rc = ensure_caller_order(f);
+    if (rc) return rc;
+    return launch_allpairs(f->stream, f->P, tap, f->pos[f->cur], f->vel[f->cur], f->n, 0, f->n, nullptr,
+                           nullptr, f->d_status, out);
+}
+
+}  // namespace
+
+// accessors used by fp_shard.cu
+namespace fp {
+FlockView flock_view(fp_flock *f) {
+    FlockView v;
+    v.stream = f->stream;
+    v.P = &f->P;
+    v.pos[0] = f->pos[0]; v.pos[1] = f->pos[1];
+    v.vel[0] = f->vel[0]; v.vel[1] = f->vel[1];
+    v.cur = &f->cur;
+    v.n = &f->n;
+    v.cap = f->cap;
+    v.permuted = &f->permuted;
+    v.status = f->d_status;
+    v.grid = &f->grid;
+    v.work = &f->work;
+    v.first_index = f->first_index;
+    v.method = f->method;
+    v.cfg = &f->cfg;
+    return v;
+}
+int flock_grid_prepare_fit(fp_flock *f) {
+    if (!f->grid_valid || (!f->domain_user && f->steps_since_fit >= 256)) return fit_grid(f);
+    return FP_OK;
+}
+void flock_count_steps(fp_flock *f, uint64_t k) { f->steps_since_fit += k; }
+}  // namespace fp
+
+// ---- C ABI ----------------------------------------------------------------------
+extern "C" {
+
+const char *fp_last_error(void) { return t_error.c_str(); }
+const char *fp_version(void) { return "feriphys-cuda 0.1.0 sm_100a"; }
+uint64_t fp_launch_count(void) { return g_launches.load(); }
+
+int fp_config_default(fp_config *cfg) {
+    if (!cfg) { set_error("null config"); return FP_ERR_INVALID; }
+    // Duration::from_millis(1).as_secs_f32() = 0f32 + 1_000_000f32 / 1e9f32
+    cfg->dt = 0.0f + 1000000.0f / 1000000000.0f;
+    cfg->avoidance_factor = 1.0f;
+    cfg->centering_factor = 0.1f;
+    cfg->velocity_matching_factor = 0.5f;
+    cfg->distance_weight_threshold = 15.0f;
+    cfg->distance_weight_threshold_falloff = 1.0f;
+    cfg->max_sight_angle = 3.14159274101257324f / 2.0f;
+    cfg->max_sight_angle_to_lead_boid = 3.14159274101257324f;
+    cfg->time_to_start_steering_secs = 4;
+    cfg->time_to_start_steering_nanos = 0;
+    cfg->steering_overrides = 0;
+    return FP_OK;
+}
+
+static int create_common(fp_flock **out, const fp_config *cfg, uint64_t n_global, uint64_t first,
+                         uint64_t n_local, const float *state, int device, uint32_t cap) {
+    if (!out) { set_error("null out pointer"); return FP_ERR_INVALID; }
+    *out = nullptr;
+    if (n_global >= (1ull << 31) || (n_local && !state)) {
+        set_error("flock size must be < 2^31 and state must be non-null");
+        return FP_ERR_INVALID;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        set_error(std::string("no usable CUDA device ") + std::to_string(device) + ": " +
+                  (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") +
+                  " -- this library has no CPU fallback");
+        return FP_ERR_CUDA;
+    }
+    FP_CUDA(cudaSetDevice(device));
+    fp_flock *f = new (std::nothrow) fp_flock();
+    if (!f) { set_error("out of host memory"); return FP_ERR_INVALID; }
+    f->device = device;
+    f->n = (uint32_t)n_local;
+    f->cap = std::max<uint32_t>(cap, (uint32_t)n_local);
+    f->n_global = n_global;
+    f->first_index = (uint32_t)first;
+    if (cfg) f->cfg = *cfg; else fp_config_default(&f->cfg);
+    derive_params(f->cfg, f->P);
+    int rc = FP_OK;
+    auto fail = [&](int code) { fp_flock_destroy(f); return code; };
+    if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(cuda_fail(cudaGetLastError(), "cudaStreamCreate", __FILE__, __LINE__));
+    for (int b = 0; b < 2; ++b) {
+        if ((rc = dev_alloc(&f->pos[b], f->cap)) || (rc = dev_alloc(&f->vel[b], f->cap))) return fail(rc);
+    }
+    if ((rc = dev_alloc(&f->d_status, 1)) || (rc = dev_alloc(&f->d_census, 4)) ||
+        (rc = dev_alloc(&f->d_bounds, 6)))
+        return fail(rc);
+    cudaMemsetAsync(f->d_status, 0, sizeof(unsigned), f->stream);
+    for (auto &ev : f->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess)
+            return fail(cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__));
+    refresh_tables(f);
+    if (n_local) {
+        if ((rc = ensure_stage(f, n_local * 6 * sizeof(float)))) return fail(rc);
+        if (cudaMemcpyAsync(f->d_stage, state, n_local * 6 * sizeof(float), cudaMemcpyHostToDevice,
+                            f->stream) != cudaSuccess)
+            return fail(cuda_fail(cudaGetLastError(), "cudaMemcpyAsync", __FILE__, __LINE__));
+        if ((rc = launch_aos6_to_soa(f->stream, (const float *)f->d_stage, f->pos[0], f->vel[0], f->n,
+                                     f->first_index)))
+            return fail(rc);
+    }
+    if (cudaStreamSynchronize(f->stream) != cudaSuccess)
+        return fail(cuda_fail(cudaGetLastError(), "cudaStreamSynchronize", __FILE__, __LINE__));
+    *out = f;
+    return FP_OK;
+}
+
+int fp_flock_create(fp_flock **out, const fp_config *cfg, uint64_t n, const float *state_aos6,
+                    int device) {
+    return create_common(out, cfg, n, 0, n, state_aos6, device, (uint32_t)n);
+}
+
+int fp_flock_create_sharded(fp_flock **out, const fp_config *cfg, uint64_t n_global,
+                            uint64_t first_index, uint64_t n_local, const float *state_aos6,
+                            int device, int rank, int world, const uint8_t nccl_unique_id[128]) {
+    if (world < 1 || rank < 0 || rank >= world || first_index + n_local > n_global) {
+        set_error("bad rank/world/first_index");
+        return FP_ERR_INVALID;
+    }
+    if (world == 1) return create_common(out, cfg, n_global, 0, n_local, state_aos6, device,
+                                         (uint32_t)n_local);
+    // slabs are unbalanced by nature: leave head-room for migration and halos
+    const uint64_t cap64 = std::min<uint64_t>(n_global, (n_global / world) * 3 / 2 + (1u << 16));
+    int rc = create_common(out, cfg, n_global, first_index, n_local, state_aos6, device,
+                           (uint32_t)std::max<uint64_t>(cap64, n_local));
+    if (rc) return rc;
+    rc = shard_create(&(*out)->shard, *out, rank, world, nccl_unique_id);
+    if (rc) {
+        fp_flock_destroy(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+int fp_flock_destroy(fp_flock *f) {
+    if (!f) return FP_OK;
+    cudaSetDevice(f->device);
+    if (f->stream) cudaStreamSynchronize(f->stream);
+    if (f->shard) shard_destroy(f->shard);
+    for (int b = 0; b < 2; ++b) { dev_free(f->pos[b]); dev_free(f->vel[b]); }
+    dev_free(f->d_leads); dev_free(f->d_attr); dev_free(f->d_obs); dev_free(f->d_lead_table);
+    dev_free(f->d_status); dev_free(f->d_census); dev_free(f->d_bounds);
+    free_grid_work(f);
+    if (f->d_stage) cudaFree(f->d_stage);
+    for (auto &ev : f->ev) if (ev) cudaEventDestroy(ev);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    delete f;
+    return FP_OK;
+}
+
+uint64_t fp_flock_len(const fp_flock *f) { return f ? (f->shard ? f->n_global : f->n) : 0; }
+
+int fp_flock_set_config(fp_flock *f, const fp_config *cfg) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (!cfg) { set_error("null config"); return FP_ERR_INVALID; }
+    const float old_reach = reach_of(f->cfg);
+    f->cfg = *cfg;
+    derive_params(f->cfg, f->P);
+    if (reach_of(f->cfg) != old_reach) f->grid_valid = false;
+    return FP_OK;
+}
+
+int fp_flock_get_config(fp_flock *f, fp_config *cfg) {
+    if (!f || !cfg) { set_error("null argument"); return FP_ERR_INVALID; }
+    *cfg = f->cfg;
+    return FP_OK;
+}
+
+int fp_flock_set_method(fp_flock *f, int method) {
+    if (!f || method < FP_METHOD_AUTO || method > FP_METHOD_SMALL) {
+        set_error("bad method");
+        return FP_ERR_INVALID;
+    }
+    f->method = method;
+    return FP_OK;
+}
+
+int fp_flock_get_method(fp_flock *f, int *method_in_use) {
+    if (!f || !method_in_use) { set_error("null argument"); return FP_ERR_INVALID; }
+    if (f->shard) *method_in_use = shard_method(f->shard, f->method, f->cfg);
+    else *method_in_use = resolve_method(f);
+    return FP_OK;
+}
+
+int fp_flock_set_leads(fp_flock *f, uint32_t n_leads, const float *leads7) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (n_leads && !leads7) { set_error("null leads"); return FP_ERR_INVALID; }
+    std::vector<float> padded((size_t)n_leads * 8, 0.0f);
+    for (uint32_t k = 0; k < n_leads; ++k) memcpy(&padded[8 * k], leads7 + 7 * k, 7 * sizeof(float));
+    rc = upload_table(f, &f->d_leads, padded.data(), padded.size());
+    if (rc) return rc;
+    f->n_leads = n_leads;
+    dev_free(f->d_lead_table);  // a plain table replaces any per-step table
+    f->table_rows = f->table_leads = f->table_cursor = 0;
+    refresh_tables(f);
+    return FP_OK;
+}
+
+int fp_flock_set_lead_table(fp_flock *f, uint32_t steps, uint32_t n_leads, const float *table7) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (steps && n_leads && !table7) { set_error("null lead table"); return FP_ERR_INVALID; }
+    const size_t rows = (size_t)steps * n_leads;
+    std::vector<float> padded(rows * 8, 0.0f);
+    for (size_t k = 0; k < rows; ++k) memcpy(&padded[8 * k], table7 + 7 * k, 7 * sizeof(float));
+    rc = upload_table(f, &f->d_lead_table, padded.data(), padded.size());
+    if (rc) return rc;
+    f->table_rows = n_leads ? steps : 0;
+    f->table_leads = n_leads;
+    f->table_cursor = 0;
+    return FP_OK;
+}
+
+int fp_flock_set_attractors(fp_flock *f, uint32_t n, const float *a4) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (n && !a4) { set_error("null attractors"); return FP_ERR_INVALID; }
+    rc = upload_table(f, &f->d_attr, a4, (size_t)n * 4);
+    if (rc) return rc;
+    f->n_attr = n;
+    refresh_tables(f);
+    return FP_OK;
+}
+
+int fp_flock_set_obstacles(fp_flock *f, uint32_t n, const float *o4) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (n && !o4) { set_error("null obstacles"); return FP_ERR_INVALID; }
+    rc = upload_table(f, &f->d_obs, o4, (size_t)n * 4);
+    if (rc) return rc;
+    f->n_obs = n;
+    refresh_tables(f);
+    return FP_OK;
+}
+
+int fp_flock_set_bbox(fp_flock *f, const float *bbox6) {
+    if (!f) { set_error("null flock handle"); return FP_ERR_INVALID; }
+    f->P.has_bbox = bbox6 ? 1 : 0;
+    if (bbox6) memcpy(f->P.bbox, bbox6, 6 * sizeof(float));
+    return FP_OK;
+}
+
+int fp_flock_set_grid_domain(fp_flock *f, const float lo3[3], const float hi3[3]) {
+    if (!f) { set_error("null flock handle"); return FP_ERR_INVALID; }
+    if (!lo3 || !hi3) {
+        f->domain_user = false;
+    } else {
+        for (int a = 0; a < 3; ++a)
+            if (!(lo3[a] <= hi3[a]) || !std::isfinite(lo3[a]) || !std::isfinite(hi3[a])) {
+                set_error("grid domain must be finite with lo <= hi");
+                return FP_ERR_INVALID;
+            }
+        memcpy(f->user_lo, lo3, sizeof(f->user_lo));
+        memcpy(f->user_hi, hi3, sizeof(f->user_hi));
+        f->domain_user = true;
+    }
+    f->grid_valid = false;
+    return FP_OK;
+}
+
+int fp_flock_grid_info(fp_flock *f, uint32_t dims3[3], float *cell_size, uint32_t *key_bits) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (!f->grid_valid && (rc = fit_grid(f))) return rc;
+    if (dims3) for (int a = 0; a < 3; ++a) dims3[a] = (uint32_t)f->grid.dim[a];
+    if (cell_size) *cell_size = f->grid.cell;
+    if (key_bits) *key_bits = f->grid.key_bits;
+    return FP_OK;
+}
+
+int fp_flock_step(fp_flock *f, uint32_t nsteps) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (nsteps == 0) return FP_OK;
+    FP_CUDA(cudaEventRecord(f->ev[0], f->stream));
+    if (f->shard) {
+        rc = shard_step(f->shard, f, nsteps);
+        if (rc) return rc;
+        FP_CUDA(cudaEventRecord(f->ev[3], f->stream));
+        f->timed = true;
+        return FP_OK;
+    }
+    const int m = resolve_method(f);
+    if (f->n == 0) return FP_OK;
+    if (m == FP_METHOD_SMALL) {
+        rc = ensure_caller_order(f);
+        if (rc) return rc;
+        const bool table = f->d_lead_table && f->table_rows;
+        const float *rows = nullptr;
+        uint32_t nrows = 0;
+        DevParams P = f->P;
+        if (table) {
+            const uint32_t row = std::min(f->table_cursor, f->table_rows - 1);
+            rows = f->d_lead_table + (size_t)row * f->table_leads * 8;
+            nrows = f->table_rows - row;
+            P.n_leads = (int)f->table_leads;
+            P.leads = rows;
+        }
+        FP_CUDA(cudaEventRecord(f->ev[1], f->stream));
+        rc = launch_small(f->stream, P, f->pos[f->cur], f->vel[f->cur], f->n, nsteps, rows, nrows,
+                          f->d_status);
+        if (rc) return rc;
+        FP_CUDA(cudaEventRecord(f->ev[2], f->stream));
+        f->table_cursor += nsteps;
+    } else {
+        for (uint32_t s = 0; s < nsteps; ++s) {
+            select_leads(f);
+            const bool last = (s + 1 == nsteps);
+            if (m == FP_METHOD_GRID) {
+                rc = grid_prepare(f);
+                if (rc) return rc;
+                if (last) FP_CUDA(cudaEventRecord(f->ev[1], f->stream));
+                // sorted copy is in pos[cur^1]; the walk overwrites the old buffer
+                rc = launch_grid_walk(f->stream, f->P, f->grid, TAP_STEP, f->pos[f->cur ^ 1],
+                                      f->vel[f->cur ^ 1], f->work.cell_start, f->n, f->pos[f->cur],
+                                      f->vel[f->cur], f->d_status, TapOut{}, nullptr);
+                if (rc) return rc;
+                f->permuted = true;
+                ++f->steps_since_fit;
+            } else {
+                rc = ensure_caller_order(f);
+                if (rc) return rc;
+                if (last) FP_CUDA(cudaEventRecord(f->ev[1], f->stream));
+                rc = launch_allpairs(f->stream, f->P, TAP_STEP, f->pos[f->cur], f->vel[f->cur], f->n, 0,
+                                     f->n, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], f->d_status, TapOut{});
+                if (rc) return rc;
+                f->cur ^= 1;
+            }
+            if (last) FP_CUDA(cudaEventRecord(f->ev[2], f->stream));
+            ++f->table_cursor;
+        }
+    }
+    FP_CUDA(cudaEventRecord(f->ev[3], f->stream));
+    f->timed = true;
+    return FP_OK;
+}
+
+int fp_flock_sync(fp_flock *f) {
+    int rc = check(f);
+    if (rc) return rc;
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    return FP_OK;
+}
+
+int fp_flock_last_step_ms(fp_flock *f, float *total_ms, float *sort_ms, float *influence_ms) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (!f->timed) { set_error("no step has been timed yet"); return FP_ERR_INVALID; }
+    FP_CUDA(cudaEventSynchronize(f->ev[3]));
+    float t = 0, s = 0, w = 0;
+    FP_CUDA(cudaEventElapsedTime(&t, f->ev[0], f->ev[3]));
+    if (!f->shard) {
+        // ev[1], ev[2] bracket the influence kernel of the LAST step of the call
+        FP_CUDA(cudaEventElapsedTime(&w, f->ev[1], f->ev[2]));
+        s = 0;
+    }
+    if (total_ms) *total_ms = t;
+    if (sort_ms) *sort_ms = s;
+    if (influence_ms) *influence_ms = w;
+    return FP_OK;
+}
+
+int fp_flock_status(fp_flock *f, uint32_t *flags) {
+    int rc = check(f);
+    if (rc) return rc;
+    unsigned v = 0;
+    FP_CUDA(cudaMemcpyAsync(&v, f->d_status, sizeof(v), cudaMemcpyDeviceToHost, f->stream));
+    FP_CUDA(cudaMemsetAsync(f->d_status, 0, sizeof(v), f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    if (flags) *flags = v;
+    return FP_OK;
+}
+
+int fp_flock_read_state(fp_flock *f, float *out) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (f->shard) return shard_read_state(f->shard, f, out);
+    if (!f->n) return FP_OK;
+    if (!out) { set_error("null output"); return FP_ERR_INVALID; }
+    const size_t bytes = (size_t)f->n * 6 * sizeof(float);
+    if ((rc = ensure_stage(f, bytes))) return rc;
+    if ((rc = launch_soa_to_aos6(f->stream, f->pos[f->cur], f->vel[f->cur], (float *)f->d_stage, f->n,
+                                 f->first_index, 1)))
+        return rc;
+    FP_CUDA(cudaMemcpyAsync(out, f->d_stage, bytes, cudaMemcpyDeviceToHost, f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    return FP_OK;
+}
+
+int fp_flock_write_state(fp_flock *f, const float *state) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (f->shard) { set_error("write_state is not supported on a sharded flock"); return FP_ERR_UNSUPPORTED; }
+    if (!f->n) return FP_OK;
+    if (!state) { set_error("null state"); return FP_ERR_INVALID; }
+    const size_t bytes = (size_t)f->n * 6 * sizeof(float);
+    if ((rc = ensure_stage(f, bytes))) return rc;
+    FP_CUDA(cudaMemcpyAsync(f->d_stage, state, bytes, cudaMemcpyHostToDevice, f->stream));
+    if ((rc = launch_aos6_to_soa(f->stream, (const float *)f->d_stage, f->pos[f->cur], f->vel[f->cur],
+                                 f->n, f->first_index)))
+        return rc;
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    f->permuted = false;
+    if (!f->domain_user) f->grid_valid = false;
+    return FP_OK;
+}
+
+static int read_instances(fp_flock *f, float *out, int raw) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (f->shard) { set_error("instance export of a sharded flock: use fp_flock_read_local"); return FP_ERR_UNSUPPORTED; }
+    if (!f->n) return FP_OK;
+    if (!out) { set_error("null output"); return FP_ERR_INVALID; }
+    const size_t bytes = (size_t)f->n * (raw ? 25 : 8) * sizeof(float);
+    if ((rc = ensure_stage(f, bytes))) return rc;
+    if ((rc = launch_instances(f->stream, f->pos[f->cur], f->vel[f->cur], (float *)f->d_stage, f->n,
+                               f->first_index, raw)))
+        return rc;
+    FP_CUDA(cudaMemcpyAsync(out, f->d_stage, bytes, cudaMemcpyDeviceToHost, f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    return FP_OK;
+}
+int fp_flock_read_instances(fp_flock *f, float *out8) { return read_instances(f, out8, 0); }
+int fp_flock_read_instances_raw(fp_flock *f, float *out25) { return read_instances(f, out25, 1); }
+
+int fp_flock_read_accel(fp_flock *f, float *out_accel3, float *out_comp15) {
+    int rc = check(f);
+    if (rc) return rc;
+    const uint64_t n = f->shard ? f->n_global : f->n;
+    if (!n) return FP_OK;
+    if (!out_accel3) { set_error("null output"); return FP_ERR_INVALID; }
+    const size_t fl = (size_t)n * (out_comp15 ? 18 : 3);
+    if ((rc = ensure_stage(f, fl * sizeof(float)))) return rc;
+    FP_CUDA(cudaMemsetAsync(f->d_stage, 0, fl * sizeof(float), f->stream));
+    TapOut t{};
+    t.accel3 = (float *)f->d_stage;
+    t.comp15 = out_comp15 ? (float *)f->d_stage + 3 * n : nullptr;
+    if ((rc = run_tap(f, TAP_ACCEL, t))) return rc;
+    FP_CUDA(cudaMemcpyAsync(out_accel3, t.accel3, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+    if (out_comp15)
+        FP_CUDA(cudaMemcpyAsync(out_comp15, t.comp15, n * 15 * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    return FP_OK;
+}
+
+int fp_flock_read_neighbors(fp_flock *f, uint32_t *out_count, uint64_t *out_hash) {
+    int rc = check(f);
+    if (rc) return rc;
+    const uint64_t n = f->shard ? f->n_global : f->n;
+    if (!n) return FP_OK;
+    if (!out_count || !out_hash) { set_error("null output"); return FP_ERR_INVALID; }
+    const size_t bytes = (size_t)n * 12;
+    if ((rc = ensure_stage(f, bytes))) return rc;
+    FP_CUDA(cudaMemsetAsync(f->d_stage, 0, bytes, f->stream));
+    TapOut t{};
+    t.nbr_hash = (unsigned long long *)f->d_stage;
+    t.nbr_count = (uint32_t *)((char *)f->d_stage + (size_t)n * 8);
+    if ((rc = run_tap(f, TAP_NEIGHBORS, t))) return rc;
+    FP_CUDA(cudaMemcpyAsync(out_hash, t.nbr_hash, n * 8, cudaMemcpyDeviceToHost, f->stream));
+    FP_CUDA(cudaMemcpyAsync(out_count, t.nbr_count, n * 4, cudaMemcpyDeviceToHost, f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    return FP_OK;
+}
+
+int fp_flock_pair_census(fp_flock *f, uint64_t out4[4]) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (!out4) { set_error("null output"); return FP_ERR_INVALID; }
+    FP_CUDA(cudaMemsetAsync(f->d_census, 0, 4 * sizeof(unsigned long long), f->stream));
+    TapOut t{};
+    t.census = f->d_census;
+    if (f->n || f->shard) {
+        if ((rc = run_tap(f, TAP_CENSUS, t))) return rc;
+    }
+    FP_CUDA(cudaMemcpyAsync(out4, f->d_census, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    return FP_OK;
+}
+
+int fp_flock_device_state(fp_flock *f, const void **pos4, const void **vel4) {
+    if (!f) { set_error("null flock handle"); return FP_ERR_INVALID; }
+    if (pos4) *pos4 = f->pos[f->cur];
+    if (vel4) *vel4 = f->vel[f->cur];
+    return FP_OK;
+}
+
+// State<boid>::euler_step / rk4_step with the acceleration accumulated first
+static int flock_state_step(fp_flock *f, float h, int rk4) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (f->shard) { set_error("State integrators are single-GPU"); return FP_ERR_UNSUPPORTED; }
+    if (!f->n) return FP_OK;
+    if ((rc = ensure_stage(f, (size_t)f->n * 3 * sizeof(float)))) return rc;
+    TapOut t{};
+    t.accel3 = (float *)f->d_stage;
+    if ((rc = run_tap(f, TAP_ACCEL, t))) return rc;
+    return launch_flock_state_step(f->stream, f->pos[f->cur], f->vel[f->cur], t.accel3, f->n,
+                                   f->first_index, h, rk4);
+}
+int fp_flock_state_euler(fp_flock *f, float h) { return flock_state_step(f, h, 0); }
+int fp_flock_state_rk4(fp_flock *f, float h) { return flock_state_step(f, h, 1); }
+
+static int combine(int device, size_t n, const float *const *in, int nin, float h, float *out, int rk4) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        set_error("no usable CUDA device -- this library has no CPU fallback");
+        return FP_ERR_CUDA;
+    }
+    if (!n) return FP_OK;
+    for (int k = 0; k < nin; ++k)
+        if (!in[k]) { set_error("null input"); return FP_ERR_INVALID; }
+    if (!out) { set_error("null output"); return FP_ERR_INVALID; }
+    FP_CUDA(cudaSetDevice(device));
+    float *d = nullptr;
+    FP_CUDA(cudaMalloc((void **)&d, (size_t)(nin + 1) * n * sizeof(float)));
+    int rc = FP_OK;
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < nin && e == cudaSuccess; ++k)
+        e = cudaMemcpy(d + (size_t)k * n, in[k], n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        float *o = d + (size_t)nin * n;
+        rc = rk4 ? launch_state_combine_rk4(0, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n, h, o, n)
+                 : launch_state_combine_euler(0, d, d + n, h, o, n);
+        if (!rc) e = cudaMemcpy(out, o, n * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "state combine", __FILE__, __LINE__);
+    return rc;
+}
+
+int fp_state_euler_combine(int device, size_t n, const float *s, const float *ds, float h, float *out) {
+    const float *in[2] = {s, ds};
+    return combine(device, n, in, 2, h, out, 0);
+}
+int fp_state_rk4_combine(int device, size_t n, const float *s, const float *k1, const float *k2,
+                         const float *k3, const float *k4, float h, float *out) {
+    const float *in[5] = {s, k1, k2, k3, k4};
+    return combine(device, n, in, 5, h, out, 1);
+}
+
+int fp_nccl_unique_id(uint8_t out128[128]) { return shard_unique_id(out128); }
+
+int fp_flock_local_len(fp_flock *f, uint64_t *n_local) {
+    if (!f || !n_local) { set_error("null argument"); return FP_ERR_INVALID; }
+    *n_local = f->n;
+    return FP_OK;
+}
+
+int fp_flock_read_local(fp_flock *f, uint64_t *out_index, float *out_aos6) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (!f->n) return FP_OK;
+    if (!out_index || !out_aos6) { set_error("null output"); return FP_ERR_INVALID; }
+    const size_t bytes = (size_t)f->n * 6 * sizeof(float);
+    if ((rc = ensure_stage(f, bytes))) return rc;
+    if ((rc = launch_soa_to_aos6(f->stream, f->pos[f->cur], f->vel[f->cur], (float *)f->d_stage, f->n,
+                                 0, 0)))
+        return rc;
+    FP_CUDA(cudaMemcpyAsync(out_aos6, f->d_stage, bytes, cudaMemcpyDeviceToHost, f->stream));
+    std::vector<float4> p(f->n);
+    FP_CUDA(cudaMemcpyAsync(p.data(), f->pos[f->cur], (size_t)f->n * sizeof(float4), cudaMemcpyDeviceToHost,
+                            f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    for (uint32_t i = 0; i < f->n; ++i) {
+        uint32_t u;
+        memcpy(&u, &p[i].w, 4);
+        out_index[i] = u;
+    }
+    return FP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+// fp_grid.cu -- K2b/K3: uniform-grid variant of the influence pass.
+//
+// The reference is all-pairs only (flocking.rs:133-151).  Because a
+// pair contributes exactly zero once dist >= thr + falloff (boid.rs:154-157),
+// restricting each boid to the 27 cells around it is EXACT provided the cell
+// edge exceeds that reach: the same f32 predicates decide the same pairs.
+//
+// Per step: cell keys + per-cell counts -> exclusive scan (cell_start) ->
+// stable radix sort of (key, slot) -> gather into sorted SoA -> 27-cell walk
+// fused with lead/attractor/bbox/steering terms and the Euler update.  The
+// state stays in sorted order between steps (pos.w carries the caller index),
+// so every global access of the next step is coalesced.
+#include "fp_internal.h"
+
+namespace fp {
+
+constexpr int GB = 256;
+
+__device__ __forceinline__ int cell_coord(float x, float origin, float inv_cell, int dim) {
+    // monotone in x: fl(x - o) , fl(. * inv), floor, clamp are all monotone
+    const int c = __float2int_rd(fmul(fsub(x, origin), inv_cell));  // NaN -> 0, saturating
+    return min(max(c, 0), dim - 1);
+}
+
+__global__ void __launch_bounds__(GB)
+grid_keys_kernel(const GridDesc g, const float4 *__restrict__ pos, uint32_t n,
+                 uint32_t *__restrict__ keys, uint32_t *__restrict__ cell_count) {
+    const uint32_t i = blockIdx.x * GB + threadIdx.x;
+    const bool valid = i < n;
+    uint32_t key = 0xffffffffu;
+    if (valid) {
+        const float4 p = pos[i];
+        const int cx = cell_coord(p.x, g.origin[0], g.inv_cell, g.dim[0]);
+        const int cy = cell_coord(p.y, g.origin[1], g.inv_cell, g.dim[1]);
+        const int cz = cell_coord(p.z, g.origin[2], g.inv_cell, g.dim[2]);
+        key = (uint32_t)((cz * g.dim[1] + cy) * g.dim[0] + cx);
+        keys[i] = key;
+    }
+    // neighbouring slots usually share a cell: one atomic per distinct key per warp
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (valid && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(cell_count + key, __popc(peers));
+}
+
+int launch_grid_keys(cudaStream_t st, const GridDesc &g, const float4 *pos, uint32_t n, GridWork &w) {
+    FP_CUDA(cudaMemsetAsync(w.cell_start, 0, ((size_t)g.ncells + 1) * sizeof(uint32_t), st));
+    if (n) {
+        grid_keys_kernel<<<(n + GB - 1) / GB, GB, 0, st>>>(g, pos, n, w.keys[0], w.cell_start);
+        count_launch();
+        FP_CUDA(cudaGetLastError());
+    }
+    return launch_exclusive_scan(st, w.cell_start, (size_t)g.ncells + 1, w.scan_tmp);
+}
+
+__global__ void __launch_bounds__(GB)
+grid_reorder_kernel(const uint32_t *__restrict__ vals, const float4 *__restrict__ pos_in,
+                    const float4 *__restrict__ vel_in, float4 *__restrict__ pos_out,
+                    float4 *__restrict__ vel_out, uint32_t n) {
+    const uint32_t i = blockIdx.x * GB + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t src = vals[i];
+    pos_out[i] = pos_in[src];
+    vel_out[i] = vel_in[src];
+}
+
+int launch_grid_reorder(cudaStream_t st, const uint32_t *vals, const float4 *pos_in,
+                        const float4 *vel_in, float4 *pos_out, float4 *vel_out, uint32_t n) {
+    if (!n) return FP_OK;
+    grid_reorder_kernel<<<(n + GB - 1) / GB, GB, 0, st>>>(vals, pos_in, vel_in, pos_out, vel_out, n);
+    count_launch();
+    FP_CUDA(cudaGetLastError());
+    return FP_OK;
+}
+
+// K3: one thread per boid of the sorted state.  For each of the 9 (dy, dz) rows
+// the cells cx-1 .. cx+1 are one contiguous slot range of the sorted arrays.
+// Accumulation order: rows (dz, dy) ascending, then slot ascending -- fixed.
+constexpr int WALK_BLOCK = 128;
+
+template <int TAP>
+__global__ void __launch_bounds__(WALK_BLOCK)
+grid_walk_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__ pos_s,
+                 const float4 *__restrict__ vel_s, const uint32_t *__restrict__ cell_start,
+                 uint32_t n_all, float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
+                 unsigned *__restrict__ status, TapOut tap) {
+    const uint32_t s = blockIdx.x * WALK_BLOCK + threadIdx.x;
+    const bool active = s < n_all;
+    unsigned long long c_far = 0, c_cull = 0, c_in = 0;
+    V3 acc = v3zero();
+    uint32_t n_count = 0;
+    unsigned long long n_hash = 0;
+    float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
+    Self self;
+    if (active) {
+        pi4 = pos_s[s];
+        vi4 = vel_s[s];
+        self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
+        const bool ghost = __float_as_uint(vi4.w) != 0u;  // halo copy owned by another rank
+        const bool need_pairs = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
+        if (need_pairs) {
+            const int cx = cell_coord(pi4.x, g.origin[0], g.inv_cell, g.dim[0]);
+            const int cy = cell_coord(pi4.y, g.origin[1], g.inv_cell, g.dim[1]);
+            const int cz = cell_coord(pi4.z, g.origin[2], g.inv_cell, g.dim[2]);
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+            for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dim[2] - 1); ++z) {
+                for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+                    const uint32_t rowbase = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
+                    const uint32_t jb = __ldg(cell_start + rowbase + x0);
+                    const uint32_t je = __ldg(cell_start + rowbase + x1 + 1);
+                    for (uint32_t j = jb; j < je; ++j) {
+                        const float4 pj = __ldg(pos_s + j);
+                        if (TAP == TAP_STEP || TAP == TAP_ACCEL) {
+                            V3 d;
+                            const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
+                            if (m2 >= P.m2_cut) continue;
+                            const float4 vj = __ldg(vel_s + j);
+                            V3 contrib;
+                            if (pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar,
+                                                    contrib))
+                                acc = vadd(acc, contrib);
+                        } else {
+                            const float4 vj = __ldg(vel_s + j);
+                            bool equal;
+                            const int o = pair_outcome(P, self, v3(pj.x, pj.y, pj.z),
+                                                       v3(vj.x, vj.y, vj.z), equal);
+                            if (equal) continue;
+                            if (TAP == TAP_NEIGHBORS) {
+                                if (o == PAIR_CONTRIB) {
+                                    ++n_count;
+                                    n_hash += mix64((unsigned long long)__float_as_uint(pj.w));
+                                }
+                            } else {
+                                c_far += (o == PAIR_FAR);
+                                c_cull += (o == PAIR_CULLED);
+                                c_in += (o == PAIR_CONTRIB);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    if (TAP == TAP_CENSUS) {
+        for (int off = 16; off > 0; off >>= 1) {
+            c_far += __shfl_down_sync(0xffffffffu, c_far, off);
+            c_cull += __shfl_down_sync(0xffffffffu, c_cull, off);
+            c_in += __shfl_down_sync(0xffffffffu, c_in, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(tap.census + 0, c_far);
+            atomicAdd(tap.census + 1, c_cull);
+            atomicAdd(tap.census + 2, c_in);
+            atomicAdd(tap.census + 3, c_far + c_cull + c_in);
+        }
+        return;
+    }
+    if (!active) return;
+    const bool ghost = __float_as_uint(vi4.w) != 0u;
+    if (ghost) {
+        if (TAP == TAP_STEP) {  // keep the slot well-defined; dropped by the next exchange
+            pos_out[s] = pi4;
+            vel_out[s] = vi4;
+        }
+        return;
+    }
+    const uint32_t idx = __float_as_uint(pi4.w);
+    if (TAP == TAP_NEIGHBORS) {
+        tap.nbr_count[idx] = n_count;
+        tap.nbr_hash[idx] = n_hash;
+        return;
+    }
+    Extras e;
+    unsigned flags = 0;
+    const V3 a = accel_total(P, self, acc, e, flags);
+    if (TAP == TAP_ACCEL) {
+        float *o = tap.accel3 + 3ull * idx;
+        o[0] = a.x; o[1] = a.y; o[2] = a.z;
+        if (tap.comp15) {
+            float *c = tap.comp15 + 15ull * idx;
+            c[0] = acc.x; c[1] = acc.y; c[2] = acc.z;
+            c[3] = e.lead.x; c[4] = e.lead.y; c[5] = e.lead.z;
+            c[6] = e.attr.x; c[7] = e.attr.y; c[8] = e.attr.z;
+            c[9] = e.bbox.x; c[10] = e.bbox.y; c[11] = e.bbox.z;
+            c[12] = e.steer.x; c[13] = e.steer.y; c[14] = e.steer.z;
+        }
+        if (flags) atomicOr(status, flags);
+        return;
+    }
+    V3 np, nv;
+    euler(P, self.p, self.v, a, np, nv);
+    pos_out[s] = make_float4(np.x, np.y, np.z, pi4.w);
+    vel_out[s] = make_float4(nv.x, nv.y, nv.z, 0.0f);
+    if (flags) atomicOr(status, flags);
+}
+
+int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap,
+                     const float4 *pos_s, const float4 *vel_s, const uint32_t *cell_start,
+                     uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
+                     const TapOut &tap_out, const uint8_t *) {
+    if (!n_all) return FP_OK;
+    const dim3 grid((n_all + WALK_BLOCK - 1) / WALK_BLOCK), block(WALK_BLOCK);
+    switch (tap) {
+        case TAP_STEP:
+            grid_walk_kernel<TAP_STEP><<<grid, block, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
+                                                               pos_out, vel_out, status, tap_out);
+            break;
+        case TAP_ACCEL:
+            grid_walk_kernel<TAP_ACCEL><<<grid, block, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
+                                                                pos_out, vel_out, status, tap_out);
+            break;
+        case TAP_NEIGHBORS:
+            grid_walk_kernel<TAP_NEIGHBORS><<<grid, block, 0, st>>>(P, g, pos_s, vel_s, cell_start,
+                                                                    n_all, pos_out, vel_out, status,
+                                                                    tap_out);
+            break;
+        default:
+            grid_walk_kernel<TAP_CENSUS><<<grid, block, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
+                                                                 pos_out, vel_out, status, tap_out);
+            break;
+    }
+    count_launch();
+    FP_CUDA(cudaGetLastError());
+    return FP_OK;
+}
+
+}  // namespace fp

@@ -1,0 +1,115 @@
+// fp_internal.h -- host-side declarations shared by the translation units of
+// libferiphys_cuda.so.  Nothing here is part of the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/feriphys_cuda.h"
+#include "fp_device.cuh"
+
+namespace fp {
+
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t k = 1) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define FP_CUDA(expr)                                                          \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) return ::fp::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// Tap selector for the influence kernels.
+enum Tap {
+    TAP_STEP = 0,       // advance the state (flocking.rs:97-122)
+    TAP_ACCEL = 1,      // write total acceleration (+ components) by caller index
+    TAP_NEIGHBORS = 2,  // write |N(i)| and hash by caller index
+    TAP_CENSUS = 3      // accumulate pair-outcome counts
+};
+
+struct TapOut {
+    float *accel3;               // n x 3 (TAP_ACCEL)
+    float *comp15;               // n x 15 or NULL
+    uint32_t *nbr_count;         // n (TAP_NEIGHBORS)
+    unsigned long long *nbr_hash;  // n
+    unsigned long long *census;  // 4 counters (TAP_CENSUS)
+};
+
+// ---- uniform grid description (host + device) ------------------------------
+struct GridDesc {
+    float origin[3];
+    float inv_cell;
+    float cell;
+    int dim[3];
+    uint32_t ncells;
+    uint32_t key_bits;
+};
+
+// ---- all-pairs (fp_allpairs.cu) --------------------------------------------
+// rows [row0, row0 + nrows) of the local output against all n_all boids of
+// pos_all/vel_all.  For TAP_STEP writes pos_out/vel_out[0..nrows).
+int launch_allpairs(cudaStream_t st, const DevParams &P, int tap, const float4 *pos_all,
+                    const float4 *vel_all, uint32_t n_all, uint32_t row0, uint32_t nrows,
+                    float4 *pos_out, float4 *vel_out, unsigned *status, const TapOut &tap_out);
+
+// One CTA, `nsteps` steps in one launch, reference summation order (fp_small.cu).
+// lead_table: nsteps rows of n_leads x 8 floats, or NULL to use P.leads for every step.
+int launch_small(cudaStream_t st, const DevParams &P, float4 *pos, float4 *vel, uint32_t n,
+                 uint32_t nsteps, const float *lead_table, uint32_t lead_rows, unsigned *status);
+uint32_t small_max_boids();
+
+// ---- grid (fp_grid.cu, fp_sort.cu) -----------------------------------------
+struct GridWork {  // device scratch owned by the handle
+    uint32_t *keys[2];
+    uint32_t *vals[2];
+    uint32_t *cell_start;  // ncells + 1
+    uint32_t *tile_hist;   // radix-sort per-tile digit histograms
+    uint32_t *scan_tmp;    // block partials for the scans
+    size_t tile_hist_elems, scan_tmp_elems, cell_cap;
+    uint32_t cap;          // boid capacity of keys/vals
+};
+
+// keys[0][i] = cell key of pos[i], vals[0][i] = i; cell_start <- exclusive scan of counts
+int launch_grid_keys(cudaStream_t st, const GridDesc &g, const float4 *pos, uint32_t n, GridWork &w);
+// stable LSD radix sort of (keys[0], vals[0]) on key bits [0, key_bits); result index in *out_buf
+int launch_radix_sort(cudaStream_t st, GridWork &w, uint32_t n, uint32_t key_bits, int *out_buf);
+// pos_out[i] = pos_in[vals[i]] (same for vel)
+int launch_grid_reorder(cudaStream_t st, const uint32_t *vals, const float4 *pos_in,
+                        const float4 *vel_in, float4 *pos_out, float4 *vel_out, uint32_t n);
+// 27-cell walk over the sorted state.  Rows [row0, row0+nrows) are stepped / tapped;
+// candidates come from all n_all sorted boids (halo included when sharded).
+int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap,
+                     const float4 *pos_s, const float4 *vel_s, const uint32_t *cell_start,
+                     uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
+                     const TapOut &tap_out, const uint8_t *owned_mask);
+
+// ---- misc kernels (fp_misc.cu) ----------------------------------------------
+int launch_aos6_to_soa(cudaStream_t st, const float *aos6, float4 *pos, float4 *vel, uint32_t n,
+                       uint32_t first_index);
+// scatter by the caller index carried in pos.w (relative to first_index)
+int launch_soa_to_aos6(cudaStream_t st, const float4 *pos, const float4 *vel, float *aos6,
+                       uint32_t n, uint32_t first_index, int by_index);
+int launch_unpermute(cudaStream_t st, const float4 *pos_in, const float4 *vel_in, float4 *pos_out,
+                     float4 *vel_out, uint32_t n, uint32_t first_index);
+int launch_instances(cudaStream_t st, const float4 *pos, const float4 *vel, float *out, uint32_t n,
+                     uint32_t first_index, int raw);
+int launch_state_combine_euler(cudaStream_t st, const float *s, const float *ds, float h, float *out,
+                               size_t n);
+int launch_state_combine_rk4(cudaStream_t st, const float *s, const float *k1, const float *k2,
+                             const float *k3, const float *k4, float h, float *out, size_t n);
+// State<boid>::euler_step / rk4_step with frozen acceleration: accel3 by internal order
+int launch_flock_state_step(cudaStream_t st, float4 *pos, float4 *vel, const float *accel3_by_index,
+                            uint32_t n, uint32_t first_index, float h, int rk4);
+int launch_bounds(cudaStream_t st, const float4 *pos, uint32_t n, float *out6 /*device*/);
+int launch_fill_u32(cudaStream_t st, uint32_t *p, uint32_t v, size_t n);
+// generic exclusive scan in place over n uint32 (n <= 2^28); tmp >= (n/4096 + 2) elements
+int launch_exclusive_scan(cudaStream_t st, uint32_t *data, size_t n, uint32_t *tmp);
+
+}  // namespace fp

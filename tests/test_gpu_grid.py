@@ -1,0 +1,174 @@
+"""-m gpu parity of the uniform-grid path (cell keys, radix sort, 27-cell walk)
+against the oracle, through the C ABI.
+
+Bar (BASELINE.json north_star): neighbour sets BIT-EXACT; per-step accelerations
+within 1e-5 relative (the walk sums in cell order, not index order, so the f32
+sum is rounded differently -- every term is still the exact reference term);
+100-step trajectories within max|dp| <= 1e-4 * max(1, |p|)."""
+import os
+
+import numpy as np
+import pytest
+
+from feriphys_b200 import _lib, synth
+from gpu_util import TABLES, bits, make_pair, py_config, rel_err
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+NT = os.cpu_count() or 1
+
+ACC_RTOL = 1e-5        # north_star: per-step accelerations within 1e-5 relative
+TRAJ_TOL = 1e-4        # 100-step positions: |dp| <= 1e-4 * max(1, |p|)
+
+
+def _check_flock(orc, st, c, tables, steps=100):
+    sim, sc = make_pair(c, st, _lib.METHOD_GRID, tables)
+    rc, rh, _ = orc.neighbors_rows(c, st, threads=NT, grid=True)
+    gc, gh = sim.read_neighbors()
+    assert np.array_equal(gc, rc), "neighbour counts differ"
+    assert np.array_equal(gh, rh), "neighbour sets differ"
+    ref, comp, flags = orc.accel_rows(c, sc, st, threads=NT, grid=True)
+    got, gcomp = sim.read_accel(components=True)
+    # the four per-boid extras do not depend on summation order: bit-identical
+    assert np.array_equal(bits(gcomp[:, 1:]), bits(comp[:, 1:]))
+    assert rel_err(gcomp[:, 0], comp[:, 0]) <= ACC_RTOL
+    assert rel_err(got, ref) <= ACC_RTOL
+    cen = sim.pair_census()
+    assert int(cen[2]) == int(rc.sum())
+    if steps:
+        cur = st
+        for _ in range(steps):
+            cur, _ = orc.step(c, sc, cur, threads=NT, grid=True)
+        sim.step_many(steps)
+        got = sim.read_state()
+        scale = np.maximum(1.0, np.linalg.norm(cur[:, :3], axis=1))
+        assert (np.linalg.norm(got[:, :3] - cur[:, :3], axis=1) / scale).max() <= TRAJ_TOL
+    return sim
+
+
+def test_grid_uniform_defaults_with_tables(orc):
+    st = synth.uniform_flock(20000, 200.0, seed=61)
+    sim = _check_flock(orc, st, orc.default_config(), TABLES)
+    dims, cell, bits_ = sim.grid_info()
+    assert cell > 16.0 and all(d >= 12 for d in dims)
+
+
+def test_grid_narrow_fov_short_range(orc):
+    st = synth.uniform_flock(30000, 90.0, seed=62)
+    c = orc.default_config(max_sight_angle=0.9, distance_weight_threshold=3.0,
+                           distance_weight_threshold_falloff=2.0)
+    _check_flock(orc, st, c, None, steps=20)
+
+
+def test_grid_clustered_with_outliers_and_clamping(orc):
+    # a dense blob, a few far outliers, and a user domain smaller than the flock:
+    # boids outside are clamped into edge cells and must still see exact neighbours
+    st = synth.uniform_flock(6000, 40.0, seed=63)
+    st[:50, :3] += f32(400.0)
+    st[50:60, :3] -= f32(300.0)
+    c = orc.default_config()
+    sim = _check_flock(orc, st, c, None, steps=10)
+    sim2, sc = make_pair(c, st, _lib.METHOD_GRID)
+    sim2.set_grid_domain([5, 5, 5], [35, 35, 35])
+    rc, rh, _ = orc.neighbors_rows(c, st, threads=NT, grid=True)
+    gc, gh = sim2.read_neighbors()
+    assert np.array_equal(gc, rc) and np.array_equal(gh, rh)
+
+
+def test_grid_tiny_and_degenerate_flocks(orc):
+    c = orc.default_config()
+    for n in (1, 2, 31, 33, 4097):
+        st = synth.uniform_flock(n, 30.0, seed=64 + n)
+        _check_flock(orc, st, c, None, steps=3)
+    # all boids at the same point (one cell), distinct velocities
+    st = synth.uniform_flock(300, 1e-3, seed=70)
+    _check_flock(orc, st, c, None, steps=0)
+    # exact duplicates are skipped by value equality (F8)
+    st = synth.uniform_flock(500, 30.0, seed=71)
+    st[100:200] = st[0:100]
+    _check_flock(orc, st, c, None, steps=0)
+
+
+def test_grid_matches_allpairs_and_survives_method_switches(orc):
+    c = orc.default_config()
+    st = synth.uniform_flock(5000, 100.0, seed=72)
+    sim, sc = make_pair(c, st, _lib.METHOD_GRID, TABLES)
+    cur = st
+    for method in (_lib.METHOD_GRID, _lib.METHOD_ALLPAIRS, _lib.METHOD_GRID, _lib.METHOD_GRID,
+                   _lib.METHOD_ALLPAIRS):
+        sim.set_method(method)
+        sim.step()
+        cur, _ = orc.step(c, sc, cur, threads=NT, grid=True)
+        got = sim.read_state()
+        assert np.abs(got - cur).max() <= 1e-5 * max(1.0, float(np.abs(cur).max()))
+    # neighbour sets agree between the two kernels on the evolved state
+    sim.set_method(_lib.METHOD_GRID)
+    g = sim.read_neighbors()
+    sim.set_method(_lib.METHOD_ALLPAIRS)
+    a = sim.read_neighbors()
+    assert np.array_equal(g[0], a[0]) and np.array_equal(g[1], a[1])
+
+
+def test_grid_permutation_invariance(orc):
+    c = orc.default_config()
+    st = synth.uniform_flock(8000, 120.0, seed=73)
+    perm = np.random.default_rng(0).permutation(len(st))
+    a, _ = make_pair(c, st, _lib.METHOD_GRID)
+    b, _ = make_pair(c, st[perm], _lib.METHOD_GRID)
+    ca, _ = a.read_neighbors()
+    cb, _ = b.read_neighbors()
+    assert np.array_equal(ca[perm], cb)
+    a.step_many(5)
+    b.step_many(5)
+    sa, sb = a.read_state(), b.read_state()
+    assert np.abs(sa[perm] - sb).max() <= 1e-5 * max(1.0, float(np.abs(sa).max()))
+
+
+def test_grid_config_change_refits(orc):
+    c = orc.default_config()
+    st = synth.uniform_flock(10000, 150.0, seed=74)
+    sim, sc = make_pair(c, st, _lib.METHOD_GRID)
+    sim.step()
+    cur, _ = orc.step(c, sc, st, threads=NT, grid=True)
+    c2 = orc.default_config(distance_weight_threshold=25.0, distance_weight_threshold_falloff=5.0,
+                            max_sight_angle=2.0)
+    sim.set_config(py_config(c2))
+    rc, rh, _ = orc.neighbors_rows(c2, sim.read_state(), threads=NT, grid=True)
+    gc, gh = sim.read_neighbors()
+    assert np.array_equal(gc, rc) and np.array_equal(gh, rh)
+    _, cell, _ = sim.grid_info()
+    assert cell > 30.0
+
+
+def test_c3_one_million_boids_sampled_rows(orc):
+    """Config C3: 2^20 boids, U[0,816)^3, FOV pi/2 -- neighbour sets of 8192 sampled rows
+    bit-exact against the oracle, accelerations within 1e-5, at steps 0 and 3; plus
+    size-independent properties at full size."""
+    n = 1 << 20
+    st = synth.uniform_flock(n, 816.0)
+    c = orc.default_config()
+    sim, sc = make_pair(c, st, _lib.METHOD_GRID)
+    dims, cell, kb = sim.grid_info()
+    assert list(dims) == [51, 51, 51] or all(50 <= d <= 51 for d in dims)
+
+    def sampled(state):
+        gc, gh = sim.read_neighbors()
+        ga = sim.read_accel()
+        for lo, hi in ((0, 4096), (n - 4096, n)):
+            rc, rh, _ = orc.neighbors_rows(c, state, lo, hi, threads=NT, grid=True)
+            assert np.array_equal(gc[lo:hi], rc) and np.array_equal(gh[lo:hi], rh)
+            ra, _, _ = orc.accel_rows(c, sc, state, lo, hi, threads=NT, grid=True)
+            assert rel_err(ga[lo:hi], ra) <= ACC_RTOL
+        return gc
+    gc = sampled(st)
+    # mean in-range-and-visible neighbours: ~33.5 in range, about half inside the FOV
+    assert 12 < gc.mean() < 22
+    cen = sim.pair_census()
+    assert int(cen[2]) == int(gc.sum()) and int(cen[3]) > 150 * n   # ~200 candidates per boid
+    sim.step_many(3)
+    s3 = sim.read_state()
+    assert np.isfinite(s3).all()
+    # positions advanced by dt * v exactly three times with f32 rounding (Euler, flocking.rs:116)
+    p1 = st[:, :3] + f32(c.dt) * st[:, 3:]
+    assert np.abs(s3[:, :3] - p1).max() < 1e-2
+    sampled(s3)
