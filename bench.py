@@ -1,0 +1,486 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native flocking step.
+
+A "step" is one ``Simulation::step`` (flocking.rs:97-131) over a synthetic
+flock that is already resident in HBM.  Default workload: BASELINE.json
+configs[3] (C4) -- 2^24 boids, U[0,2048)^3, radius-limited FOV-gated influence
+on the uniform-grid path -- which fits one B200 and is the configuration the
+metric "boid-steps/sec at 16M boids, 1/2/4/8 B200" is quoted on; with
+``--gpus N`` the SAME flock is slab-sharded over N ranks (strong scaling).
+Other SURVEY 8d configurations: ``--workload c1|c2|c3|c5``.
+
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU oracle (a C
+restatement of the reference's Rust loops: the reference cannot be built here,
+no Rust toolchain) on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+f32 = np.float32
+PI = float(f32(3.14159274101257324))
+
+# SURVEY.md 8d.  n, domain edge, method, config overrides, default timed steps
+WORKLOADS = {
+    "c1": dict(n=110, desc="demo scene sim 1 (demos/flocking.rs:92-121): 110 boids, 1 lead, ship obstacle",
+               method="small", steps=1000),
+    "c2": dict(n=100_000, extent=24.0, method="allpairs", steps=10,
+               desc="100k boids U[0,24)^3, all-pairs, distance-gated only (max_sight_angle=pi)"),
+    "c3": dict(n=1 << 20, extent=816.0, method="grid", steps=100,
+               desc="2^20 boids U[0,816)^3, uniform grid, FOV pi/2, defaults"),
+    "c4": dict(n=1 << 24, extent=2048.0, method="grid", steps=20,
+               desc="2^24 boids U[0,2048)^3, uniform grid, FOV pi/2, defaults, x-slab sharded"),
+    "c5": dict(n=1 << 22, extent=1296.0, method="grid", steps=20,
+               desc="2^22 boids U[0,1296)^3, 8 Lissajous leads, 8 attractors/repellers, 16 obstacles, bbox"),
+}
+
+FP32_LANES = 148 * 128  # B200: 148 SMs x 128 FP32 lanes
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--method", default=None, choices=["grid", "allpairs", "small"])
+    ap.add_argument("--n", type=int, default=None, help="override the flock size (debugging)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="cpu_baseline budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "MEASURED_PEAKS.json (measured)"
+    except Exception:
+        return 6650.0, 1965.0, "B200_PROFILING.md fallback (6.65 TB/s)"
+
+
+# ---- workload construction (host arrays shared by both arms) ----------------------
+def lissajous(k):
+    from feriphys_b200.flocking import cosf, sinf
+    a, b, c = f32(300 + 40 * k), f32(7 + k), f32(5 + 2 * k)
+
+    def path(t):
+        t = f32(t)
+        return (f32(648) + a * cosf(t / b), f32(648) + a * sinf(t / c), f32(648) + a * cosf(t / (b + c)))
+    return path
+
+
+def build_workload(name, n_override=None, first=0, count=None):
+    from feriphys_b200 import synth
+    w = dict(WORKLOADS[name])
+    w["name"] = name
+    if n_override:
+        w["n"] = n_override
+    n = w["n"]
+    cfg = {}
+    tables = {}
+    if name == "c1":
+        state = synth.spawn_flock(synth.DEMO_SIM1["spawn"], n)
+        tables["obstacles"] = synth.DEMO_OBSTACLES
+        w["lead_paths"] = "demo"
+    else:
+        cnt = n if count is None else count
+        state = synth.uniform_flock(cnt, w["extent"], first=first)
+    if name == "c2":
+        # factors scaled by 110/N keep accelerations at demo magnitude (inside the GUI ranges)
+        cfg = dict(max_sight_angle=PI, centering_factor=float(f32(0.1) * f32(110.0) / f32(n)),
+                   velocity_matching_factor=float(f32(0.5) * f32(110.0) / f32(n)))
+    if name == "c5":
+        att, obs, bbox = synth.c5_tables(w["extent"])
+        tables.update(attractors=att, obstacles=obs, bbox=bbox)
+        w["lead_paths"] = "lissajous"
+    w.update(state=state, cfg=cfg, tables=tables)
+    return w
+
+
+def make_leads(w):
+    from feriphys_b200.flocking import DEMO_PATHS, LeadBoid
+    kind = w.get("lead_paths")
+    if kind == "demo":
+        return [LeadBoid(DEMO_PATHS[0])]
+    if kind == "lissajous":
+        return [LeadBoid(lissajous(k)) for k in range(8)]
+    return None
+
+
+def py_config(cfg_over):
+    from feriphys_b200.flocking import Config
+    c = Config()
+    for k, v in cfg_over.items():
+        setattr(c, k, v)
+    return c
+
+
+# ---- clocks during the timed region -------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 6:
+                continue
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), c[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- CPU oracle legs ------------------------------------------------------------------
+class OracleRunner:
+    """Times the CPU oracle on a bounded sample of the workload's rows."""
+
+    def __init__(self, w, threads):
+        from oracle_lib import Scene, oracle
+        import ctypes as C
+        self.C = C
+        self.orc = oracle()
+        self.w = w
+        self.threads = threads
+        self.cfg = self.orc.default_config(**w["cfg"])
+        leads = make_leads(w)
+        t = w["tables"]
+        self.scene = Scene(leads=np.stack([l.row() for l in leads]) if leads else None,
+                           attractors=t.get("attractors"), obstacles=t.get("obstacles"),
+                           bbox=t.get("bbox"))
+        self.sc = self.scene.struct()
+        self.state = np.ascontiguousarray(w["state"], np.float32)
+        self.n = len(self.state)
+        self.grid = None
+        self.t_build = 0.0
+        if w["method_resolved"] == "grid":
+            t0 = time.perf_counter()
+            self.grid = self.orc.lib.orc_grid_build(C.byref(self.cfg), self.n,
+                                                    self.state.ctypes.data_as(C.c_void_p))
+            self.t_build = time.perf_counter() - t0
+
+    def rows(self, m):
+        """accelerations of rows [0, m): the per-boid work of one step. -> seconds"""
+        C = self.C
+        out = np.empty((m, 3), np.float32)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        t0 = time.perf_counter()
+        if self.grid is not None:
+            self.orc.lib.orc_grid_accel_rows(self.grid, C.byref(self.cfg), C.byref(self.sc), self.n,
+                                             P(self.state), 0, m, P(out), None, None, self.threads)
+        else:
+            self.orc.lib.orc_accel_rows(C.byref(self.cfg), C.byref(self.sc), self.n, P(self.state), 0,
+                                        m, P(out), None, None, self.threads)
+        return time.perf_counter() - t0
+
+    def pick_rows(self, seconds):
+        m0 = min(self.n, 4096 if self.grid is not None else 8 * self.threads)
+        t = max(self.rows(m0), 1e-4)
+        m = int(min(self.n, max(m0, m0 * seconds / t)))
+        return max(1, m)
+
+    def close(self):
+        if self.grid is not None:
+            self.orc.lib.orc_grid_free(self.grid)
+            self.grid = None
+
+
+def sample_text(r, m):
+    how = "grid-accelerated oracle (bit-identical to the literal loops)" if r.grid is not None \
+        else "literal O(N) rows"
+    return (f"accelerations of the first {m} of {r.n} boids per step ({how}); "
+            f"boid-steps/s = rows / seconds" +
+            (f"; one-off grid build {r.t_build:.2f}s excluded" if r.grid is not None else ""))
+
+
+def pairs_per_boid_step(census, n):
+    """in-range ordered pairs per step (grid) or all ordered pairs (all-pairs)."""
+    return float(census[1] + census[2]), float(census[3])
+
+
+# ---- reference arm ---------------------------------------------------------------------
+def run_reference(args, w, rank):
+    if rank != 0:
+        return None
+    threads = os.cpu_count() or 1
+    r = OracleRunner(w, threads)
+    steps = args.steps
+    per_step = min(3.0, 120.0 / max(1, steps + args.warmup))
+    m = r.pick_rows(per_step)
+    for _ in range(args.warmup):
+        r.rows(m)
+    t = 0.0
+    for _ in range(steps):
+        t += r.rows(m)
+    sample = sample_text(r, m)
+    r.close()
+    value = m * steps / t
+    line = {
+        "impl": "reference", "metric": "boid-steps/sec", "value": value, "unit": "boid-steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (splitmix64-keyed uniform flock, seed 0xFE21F)",
+        "config": config_block(w, args, 1),
+        "cpu_baseline": {"value": value, "unit": "boid-steps/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "boid-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = CPU oracle (C restatement of the Rust loops, OpenMP over boids); "
+                "the Rust reference cannot be built in this image (no cargo/rustc)",
+    }
+    return line
+
+
+def config_block(w, args, world):
+    return {
+        "workload": f"{w['name']}: {w['desc']}",
+        "boids": int(w["n"]), "method": w["method_resolved"],
+        "sharding": ("none" if world == 1 else
+                     (f"x-slab x{world}, halo exchange + migration" if w["method_resolved"] == "grid"
+                      else f"boid-index x{world}, all-gather of pos/vel")),
+        "l2": "inputs larger than L2 (state is %.0f MB per buffer)" % (w["n"] * 32 / 1e6)
+        if w["n"] * 32 > 126e6 else "state fits L2; no flush (FP32/latency-bound workload)",
+    }
+
+
+# ---- our arm -----------------------------------------------------------------------------
+def run_ours(args, w, rank, world, local_rank):
+    import torch
+    from feriphys_b200 import _lib
+    from feriphys_b200.flocking import Simulation, Obstacle, PointAttractor, BoundingBox
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    method = {"grid": _lib.METHOD_GRID, "allpairs": _lib.METHOD_ALLPAIRS,
+              "small": _lib.METHOD_SMALL}[w["method_resolved"]]
+    t = w["tables"]
+    kw = dict(
+        bounding_box=(BoundingBox(t["bbox"][0:2], t["bbox"][2:4], t["bbox"][4:6]) if "bbox" in t else None),
+        lead_boids=make_leads(w),
+        obstacles=[Obstacle(o[:3], float(o[3])) for o in t["obstacles"]] if "obstacles" in t else None,
+        attractors=[PointAttractor(a[:3], float(a[3])) for a in t["attractors"]] if "attractors" in t else None,
+        method=method, device=local_rank)
+    n = w["n"]
+    if world == 1:
+        sim = Simulation.from_state(w["state"], **kw)
+    else:
+        from feriphys_b200.sharded import ShardedSimulation
+        sim = ShardedSimulation.from_global_slice(w["state"], n, w["first"], dist, **kw)
+    sim.set_config(py_config(w["cfg"]))
+
+    K, W = args.steps, args.warmup
+    lib = _lib.load()
+    sim.step_many(W) if W else None
+    sim.sync()
+    census = sim.pair_census()          # outside the timed region (extra launches)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = lib.fp_launch_count()
+    sim.timing_begin()
+    t0 = time.perf_counter()
+    sim.step_many(K)
+    barrier()
+    wall = time.perf_counter() - t0
+    nst, span_ms, sort_ms, infl_ms = sim.timing_end()
+    launches = lib.fp_launch_count() - launches0
+    clocks = sampler.stop()
+    dev_s = span_ms / 1e3
+    if dist is not None:
+        tt = torch.tensor([dev_s, wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_s, wall = float(tt[0]), float(tt[1])
+        ll = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ll)
+        launches = int(ll[0])
+    value = n * K / dev_s
+
+    # ---- e2e: the drop-in call sequence with HOST buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e and world == 1:
+        host_in = torch.from_numpy(np.ascontiguousarray(w["state"])).pin_memory()
+        host_out = torch.empty_like(host_in).pin_memory()
+        a_in, a_out = host_in.numpy(), host_out.numpy()
+        ke = max(1, min(K, 10))
+        sim.write_state(a_in); sim.step_many(1); a_out[:] = sim.read_state()   # warm
+        barrier()
+        te = time.perf_counter()
+        for _ in range(ke):
+            _lib.check(lib.fp_flock_write_state(sim._h, _lib.ptr(a_in)))     # H2D
+            sim.step_many(1)
+            _lib.check(lib.fp_flock_read_state(sim._h, _lib.ptr(a_out)))     # D2H (synchronises)
+        barrier()
+        te = time.perf_counter() - te
+        e2e = {"value": n * ke / te, "unit": "boid-steps/s", "h2d_bytes_per_step": int(n * 24),
+               "d2h_bytes_per_step": int(n * 24), "steps": ke,
+               "path": "fp_flock_write_state -> fp_flock_step -> fp_flock_read_state, pinned host buffers"}
+    elif world > 1:
+        e2e = sim.e2e(K, barrier) if hasattr(sim, "e2e") else None
+
+    hbm, sm_max, peak_src = measured_peaks()
+    steps_seen = max(1, nst)
+    grid = w["method_resolved"] == "grid"
+    in_range, candidates = pairs_per_boid_step(census, n)
+    if world > 1 and dist is not None:
+        cc = torch.tensor([in_range, candidates, float(census[0]), float(census[1]), float(census[2])],
+                          device="cuda", dtype=torch.float64)
+        dist.all_reduce(cc)
+        in_range, candidates = float(cc[0]), float(cc[1])
+        census = np.array([cc[2].item(), cc[3].item(), cc[4].item(), cc[1].item()])
+    flops_step = 8.0 * float(census[0]) + 18.0 * float(census[1]) + 54.0 * float(census[2])
+    infl_s = infl_ms / 1e3 / steps_seen if w["method_resolved"] != "small" else dev_s / K
+    n_local = n / world
+    if grid:
+        roofline = {"bound": "hbm", "kernel": "grid_walk_kernel<TAP_STEP> (27-cell walk + extras + Euler)",
+                    "achieved": 64.0 * n_local / infl_s / 1e9, "peak": hbm, "unit": "GB/s",
+                    "algorithmic_bytes_per_boid": 64, "traffic": None, "peak_source": peak_src}
+    else:
+        peak = FP32_LANES * 2 * sm_max * 1e6 / 1e12
+        roofline = {"bound": "fp32", "kernel": "allpairs_kernel<TAP_STEP>" if w["method_resolved"] == "allpairs"
+                    else "small_kernel", "achieved": flops_step / world / infl_s / 1e12, "peak": peak,
+                    "unit": "TFLOP/s", "traffic": None,
+                    "peak_source": "148 SM x 128 lanes x 2 x clocks.max.sm (FMA peak; exact non-fused "
+                                   "arithmetic can reach at most half)"}
+    roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    line = {
+        "metric": "boid-steps/sec", "value": value, "unit": "boid-steps/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (splitmix64-keyed uniform flock, seed 0xFE21F)",
+        "config": config_block(w, args, world),
+        "pair_interactions_per_sec": in_range * K / dev_s,
+        "candidate_pairs_per_sec": candidates * K / dev_s,
+        "pairs": {"rejected_by_distance": float(census[0]), "fov_culled": float(census[1]),
+                  "contributing": float(census[2]), "examined": float(census[3]),
+                  "note": "ordered pairs per step, counted once on the post-warm-up state"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "timing": {"device_span_ms": span_ms, "wall_ms": wall * 1e3, "sort_phase_ms_per_step": sort_ms / steps_seen,
+                   "influence_ms_per_step": infl_ms / steps_seen,
+                   "how": "CUDA events on the library's stream, max over ranks"},
+        "roofline": roofline,
+    }
+    if grid:
+        step_s = dev_s / K
+        line["roofline_step"] = {"bound": "hbm", "achieved": 196.0 * n_local / step_s / 1e9, "peak": hbm,
+                                 "unit": "GB/s", "frac": 196.0 * n_local / step_s / 1e9 / hbm,
+                                 "algorithmic_bytes_per_boid_step": 196,
+                                 "note": "whole step (keys + sort + gather + walk), SURVEY 8d.2 byte model"}
+        peak = FP32_LANES * 2 * sm_max * 1e6 / 1e12
+        line["fp32_model"] = {"flops_per_step": flops_step, "achieved": flops_step / world / infl_s / 1e12,
+                              "peak": peak, "unit": "TFLOP/s", "frac": flops_step / world / infl_s / 1e12 / peak,
+                              "note": "8/18/54 flops per examined pair by outcome (SURVEY 8d.1) over the "
+                                      "walk kernel's time; exact unfused arithmetic caps at frac 0.5"}
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        r = OracleRunner(w, threads)
+        m = r.pick_rows(args.cpu_seconds)
+        tsec = r.rows(m)
+        line["cpu_baseline"] = {"value": m / tsec, "unit": "boid-steps/s", "cores": threads, "kind": "port",
+                                "sample": sample_text(r, m)}
+        r.close()
+    else:
+        line["cpu_baseline"] = None
+    if dist is not None:
+        dist.destroy_process_group()
+    return line if rank == 0 else None
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.impl == "reference" and rank != 0:
+        return
+    n = args.n or WORLDS_N(args.workload)
+    first, count = 0, None
+    if world > 1 and args.impl == "ours":
+        per = n // world
+        first = rank * per
+        count = per if rank < world - 1 else n - first
+    w = build_workload(args.workload, args.n, first, count)
+    w["first"] = first
+    w["method_resolved"] = args.method or w["method"]
+    if args.steps is None:
+        args.steps = w["steps"]
+    if args.impl == "reference":
+        line = run_reference(args, w, rank)
+    else:
+        line = run_ours(args, w, rank, world, local_rank)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def WORLDS_N(name):
+    return WORKLOADS[name]["n"]
+
+
+if __name__ == "__main__":
+    main()

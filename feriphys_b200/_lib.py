@@ -69,8 +69,9 @@ _PROTOS = {
     "fp_flock_set_grid_domain": (C.c_int, [_P, _P, _P]),
     "fp_flock_grid_info": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "fp_flock_device_state": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
-    "fp_flock_last_step_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float),
-                                        C.POINTER(C.c_float)]),
+    "fp_flock_timing_begin": (C.c_int, [_P]),
+    "fp_flock_timing_end": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "fp_flock_state_euler": (C.c_int, [_P, C.c_float]),
     "fp_flock_state_rk4": (C.c_int, [_P, C.c_float]),
     "fp_state_euler_combine": (C.c_int, [C.c_int, C.c_size_t, _P, _P, C.c_float, _P]),

@@ -126,8 +126,10 @@ struct fp_flock {
     // staging for host transfers
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool timed = false;
+    // timing hook: three events per step (before sort phase, before influence, after)
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    bool timing = false;
     Shard *shard = nullptr;  // multi-GPU state (fp_shard.cu)
 };
 
@@ -452,9 +454,6 @@ static int create_common(fp_flock **out, const fp_config *cfg, uint64_t n_global
         (rc = dev_alloc(&f->d_bounds, 6)))
         return fail(rc);
     cudaMemsetAsync(f->d_status, 0, sizeof(unsigned), f->stream);
-    for (auto &ev : f->ev)
-        if (cudaEventCreate(&ev) != cudaSuccess)
-            return fail(cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__));
     refresh_tables(f);
     if (n_local) {
         if ((rc = ensure_stage(f, n_local * 6 * sizeof(float)))) return fail(rc);
@@ -508,7 +507,7 @@ int fp_flock_destroy(fp_flock *f) {
     dev_free(f->d_status); dev_free(f->d_census); dev_free(f->d_bounds);
     free_grid_work(f);
     if (f->d_stage) cudaFree(f->d_stage);
-    for (auto &ev : f->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : f->ev_pool) if (ev) cudaEventDestroy(ev);
     if (f->stream) cudaStreamDestroy(f->stream);
     delete f;
     return FP_OK;
@@ -636,18 +635,28 @@ int fp_flock_grid_info(fp_flock *f, uint32_t dims3[3], float *cell_size, uint32_
     return FP_OK;
 }
 
+// timing hook: record the next pooled event on the stream (no-op unless timing)
+static int mark(fp_flock *f) {
+    if (!f->timing) return FP_OK;
+    if (f->ev_used == f->ev_pool.size()) {
+        cudaEvent_t e;
+        FP_CUDA(cudaEventCreate(&e));
+        f->ev_pool.push_back(e);
+    }
+    FP_CUDA(cudaEventRecord(f->ev_pool[f->ev_used++], f->stream));
+    return FP_OK;
+}
+}  // extern "C"
+namespace fp {
+int flock_mark(fp_flock *f) { return mark(f); }
+}
+extern "C" {
+
 int fp_flock_step(fp_flock *f, uint32_t nsteps) {
     int rc = check(f);
     if (rc) return rc;
     if (nsteps == 0) return FP_OK;
-    FP_CUDA(cudaEventRecord(f->ev[0], f->stream));
-    if (f->shard) {
-        rc = shard_step(f->shard, f, nsteps);
-        if (rc) return rc;
-        FP_CUDA(cudaEventRecord(f->ev[3], f->stream));
-        f->timed = true;
-        return FP_OK;
-    }
+    if (f->shard) return shard_step(f->shard, f, nsteps);
     const int m = resolve_method(f);
     if (f->n == 0) return FP_OK;
     if (m == FP_METHOD_SMALL) {
@@ -664,42 +673,40 @@ int fp_flock_step(fp_flock *f, uint32_t nsteps) {
             P.n_leads = (int)f->table_leads;
             P.leads = rows;
         }
-        FP_CUDA(cudaEventRecord(f->ev[1], f->stream));
+        if ((rc = mark(f)) || (rc = mark(f))) return rc;
         rc = launch_small(f->stream, P, f->pos[f->cur], f->vel[f->cur], f->n, nsteps, rows, nrows,
                           f->d_status);
         if (rc) return rc;
-        FP_CUDA(cudaEventRecord(f->ev[2], f->stream));
+        if ((rc = mark(f))) return rc;
         f->table_cursor += nsteps;
-    } else {
-        for (uint32_t s = 0; s < nsteps; ++s) {
-            select_leads(f);
-            const bool last = (s + 1 == nsteps);
-            if (m == FP_METHOD_GRID) {
-                rc = grid_prepare(f);
-                if (rc) return rc;
-                if (last) FP_CUDA(cudaEventRecord(f->ev[1], f->stream));
-                // sorted copy is in pos[cur^1]; the walk overwrites the old buffer
-                rc = launch_grid_walk(f->stream, f->P, f->grid, TAP_STEP, f->pos[f->cur ^ 1],
-                                      f->vel[f->cur ^ 1], f->work.cell_start, f->n, f->pos[f->cur],
-                                      f->vel[f->cur], f->d_status, TapOut{}, nullptr);
-                if (rc) return rc;
-                f->permuted = true;
-                ++f->steps_since_fit;
-            } else {
-                rc = ensure_caller_order(f);
-                if (rc) return rc;
-                if (last) FP_CUDA(cudaEventRecord(f->ev[1], f->stream));
-                rc = launch_allpairs(f->stream, f->P, TAP_STEP, f->pos[f->cur], f->vel[f->cur], f->n, 0,
-                                     f->n, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], f->d_status, TapOut{});
-                if (rc) return rc;
-                f->cur ^= 1;
-            }
-            if (last) FP_CUDA(cudaEventRecord(f->ev[2], f->stream));
-            ++f->table_cursor;
-        }
+        return FP_OK;
     }
-    FP_CUDA(cudaEventRecord(f->ev[3], f->stream));
-    f->timed = true;
+    for (uint32_t s = 0; s < nsteps; ++s) {
+        select_leads(f);
+        if ((rc = mark(f))) return rc;
+        if (m == FP_METHOD_GRID) {
+            rc = grid_prepare(f);
+            if (rc) return rc;
+            if ((rc = mark(f))) return rc;
+            // sorted copy is in pos[cur^1]; the walk overwrites the old buffer
+            rc = launch_grid_walk(f->stream, f->P, f->grid, TAP_STEP, f->pos[f->cur ^ 1],
+                                  f->vel[f->cur ^ 1], f->work.cell_start, f->n, f->pos[f->cur],
+                                  f->vel[f->cur], f->d_status, TapOut{}, nullptr);
+            if (rc) return rc;
+            f->permuted = true;
+            ++f->steps_since_fit;
+        } else {
+            rc = ensure_caller_order(f);
+            if (rc) return rc;
+            if ((rc = mark(f))) return rc;
+            rc = launch_allpairs(f->stream, f->P, TAP_STEP, f->pos[f->cur], f->vel[f->cur], f->n, 0,
+                                 f->n, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], f->d_status, TapOut{});
+            if (rc) return rc;
+            f->cur ^= 1;
+        }
+        if ((rc = mark(f))) return rc;
+        ++f->table_cursor;
+    }
     return FP_OK;
 }
 
@@ -710,21 +717,35 @@ int fp_flock_sync(fp_flock *f) {
     return FP_OK;
 }
 
-int fp_flock_last_step_ms(fp_flock *f, float *total_ms, float *sort_ms, float *influence_ms) {
+int fp_flock_timing_begin(fp_flock *f) {
     int rc = check(f);
     if (rc) return rc;
-    if (!f->timed) { set_error("no step has been timed yet"); return FP_ERR_INVALID; }
-    FP_CUDA(cudaEventSynchronize(f->ev[3]));
-    float t = 0, s = 0, w = 0;
-    FP_CUDA(cudaEventElapsedTime(&t, f->ev[0], f->ev[3]));
-    if (!f->shard) {
-        // ev[1], ev[2] bracket the influence kernel of the LAST step of the call
-        FP_CUDA(cudaEventElapsedTime(&w, f->ev[1], f->ev[2]));
-        s = 0;
+    f->ev_used = 0;
+    f->timing = true;
+    return FP_OK;
+}
+
+int fp_flock_timing_end(fp_flock *f, uint32_t *steps, float *span_ms, float *sort_ms,
+                        float *influence_ms) {
+    int rc = check(f);
+    if (rc) return rc;
+    f->timing = false;
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    const size_t k = f->ev_used / 3;
+    float span = 0, so = 0, in = 0;
+    for (size_t s = 0; s < k; ++s) {
+        float a = 0, b = 0;
+        FP_CUDA(cudaEventElapsedTime(&a, f->ev_pool[3 * s], f->ev_pool[3 * s + 1]));
+        FP_CUDA(cudaEventElapsedTime(&b, f->ev_pool[3 * s + 1], f->ev_pool[3 * s + 2]));
+        so += a;
+        in += b;
     }
-    if (total_ms) *total_ms = t;
-    if (sort_ms) *sort_ms = s;
-    if (influence_ms) *influence_ms = w;
+    if (k) FP_CUDA(cudaEventElapsedTime(&span, f->ev_pool[0], f->ev_pool[3 * k - 1]));
+    f->ev_used = 0;
+    if (steps) *steps = (uint32_t)k;
+    if (span_ms) *span_ms = span;
+    if (sort_ms) *sort_ms = so;
+    if (influence_ms) *influence_ms = in;
     return FP_OK;
 }
 

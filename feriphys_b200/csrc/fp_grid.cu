@@ -171,7 +171,7 @@ grid_walk_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__
     }
     Extras e;
     unsigned flags = 0;
-    const V3 a = accel_total(P, self, acc, e, flags);
+    const V3 a = accel_total(P, self, acc, e, flags, TAP == TAP_ACCEL);
     if (TAP == TAP_ACCEL) {
         float *o = tap.accel3 + 3ull * idx;
         o[0] = a.x; o[1] = a.y; o[2] = a.z;

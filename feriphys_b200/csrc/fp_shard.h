@@ -29,6 +29,7 @@ struct FlockView {
 FlockView flock_view(fp_flock *f);
 int flock_grid_prepare_fit(fp_flock *f);
 void flock_count_steps(fp_flock *f, uint64_t k);
+int flock_mark(fp_flock *f);  // timing hook event
 
 int shard_unique_id(uint8_t out128[128]);
 int shard_create(Shard **out, fp_flock *f, int rank, int world, const uint8_t id[128]);

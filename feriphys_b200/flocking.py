@@ -320,6 +320,16 @@ class Simulation:
         check(self._lib.fp_flock_read_state(self._h, ptr(out)))
         return out
 
+    def read_local(self):
+        """-> (index, state) in the library's INTERNAL order (cell-sorted after a grid
+        step): ``state[k]`` is the boid the caller knows as ``index[k]``."""
+        n = C.c_uint64(0)
+        check(self._lib.fp_flock_local_len(self._h, C.byref(n)))
+        idx = np.empty(n.value, np.uint64)
+        st = np.empty((n.value, 6), np.float32)
+        check(self._lib.fp_flock_read_local(self._h, ptr(idx), ptr(st)))
+        return idx, st
+
     def write_state(self, state) -> None:
         st = f32c(state, (self._n, 6))
         check(self._lib.fp_flock_write_state(self._h, ptr(st)))
@@ -362,10 +372,15 @@ class Simulation:
         check(self._lib.fp_flock_grid_info(self._h, ptr(dims), C.byref(cell), C.byref(bits)))
         return dims, cell.value, bits.value
 
-    def last_step_ms(self):
-        t, s, w = C.c_float(0), C.c_float(0), C.c_float(0)
-        check(self._lib.fp_flock_last_step_ms(self._h, C.byref(t), C.byref(s), C.byref(w)))
-        return t.value, s.value, w.value
+    def timing_begin(self) -> None:
+        check(self._lib.fp_flock_timing_begin(self._h))
+
+    def timing_end(self):
+        """-> (steps, span_ms, sort_ms, influence_ms) measured with CUDA events on the
+        library's stream since ``timing_begin``."""
+        n, t, s, w = C.c_uint32(0), C.c_float(0), C.c_float(0), C.c_float(0)
+        check(self._lib.fp_flock_timing_end(self._h, C.byref(n), C.byref(t), C.byref(s), C.byref(w)))
+        return n.value, t.value, s.value, w.value
 
     def state_euler(self, h: float) -> None:
         """``State::<boid>::euler_step(h)`` (state.rs:75-83) with frozen acceleration."""

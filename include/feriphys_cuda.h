@@ -134,9 +134,14 @@ int fp_flock_grid_info(fp_flock *f, uint32_t dims3[3], float *cell_size, uint32_
  * (ADDITION).  pos4/vel4 are the SoA float4 arrays of the current state in
  * INTERNAL order; pos4[i].w carries the caller index as uint32 bits. */
 int fp_flock_device_state(fp_flock *f, const void **pos4, const void **vel4);
-/* Timing hook: CUDA-event milliseconds spent in the kernels of the last
- * fp_flock_step call, split by kernel family (sort, reorder, influence). */
-int fp_flock_last_step_ms(fp_flock *f, float *total_ms, float *sort_ms, float *influence_ms);
+/* Timing hook (ADDITION): between _begin and _end every step records CUDA
+ * events on the handle's stream around its sort phase (keys, scan, radix sort,
+ * gather) and its influence kernel.  _end synchronises and returns the number
+ * of steps seen, the device time from the first event to the last (span_ms)
+ * and the summed durations of the two phases. */
+int fp_flock_timing_begin(fp_flock *f);
+int fp_flock_timing_end(fp_flock *f, uint32_t *steps, float *span_ms, float *sort_ms,
+                        float *influence_ms);
 
 /* State<T>::euler_step / rk4_step (src/simulation/state.rs:75-106) over the
  * flock viewed as a Stateful with 6 elements [px py pz vx vy vz] whose
