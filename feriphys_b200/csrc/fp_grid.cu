@@ -10,17 +10,13 @@
 // fused with lead/attractor/bbox/steering terms and the Euler update.  The
 // state stays in sorted order between steps (pos.w carries the caller index),
 // so every global access of the next step is coalesced.
-#include "fp_internal.h"
+#include <stdlib.h>
+
+#include "fp_grid.cuh"
 
 namespace fp {
 
 constexpr int GB = 256;
-
-__device__ __forceinline__ int cell_coord(float x, float origin, float inv_cell, int dim) {
-    // monotone in x: fl(x - o) , fl(. * inv), floor, clamp are all monotone
-    const int c = __float2int_rd(fmul(fsub(x, origin), inv_cell));  // NaN -> 0, saturating
-    return min(max(c, 0), dim - 1);
-}
 
 __global__ void __launch_bounds__(GB)
 grid_keys_kernel(const GridDesc g, const float4 *__restrict__ pos, uint32_t n,
@@ -155,42 +151,100 @@ grid_walk_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__
         return;
     }
     if (!active) return;
-    const bool ghost = __float_as_uint(vi4.w) != 0u;
-    if (ghost) {
-        if (TAP == TAP_STEP) {  // keep the slot well-defined; dropped by the next exchange
-            pos_out[s] = pi4;
-            vel_out[s] = vi4;
+    walk_finish<TAP>(P, s, pi4, vi4, self, acc, n_count, n_hash, pos_out, vel_out, status, tap);
+}
+
+// K3 (production form for TAP_STEP / TAP_ACCEL): same thread-per-boid walk, same
+// arithmetic and the same summation order as grid_walk_kernel above, but split into
+// three warp-convergent phases so lanes are not idled by the distance and FOV branches
+// (ncu on the one-phase kernel: 9.7 of 32 threads active per instruction):
+//   1. gate   -- every candidate: m2 against m2_cut; survivors' slots are appended to
+//                a per-thread list in shared memory ([entry][thread]: bank == lane, so
+//                any mix of per-lane entry indices is conflict-free);
+//   2. FOV    -- survivors only: exact cosine against cstar; list compacted in place;
+//   3. forces -- visible neighbours only: pair_inrange, accumulated in list (= slot) order.
+// A full list is drained (phases 2+3) before the next chunk of candidates, warp-uniformly.
+constexpr int W2_BLOCK = 128;
+constexpr int W2_CAP = 64;
+
+template <int TAP>
+__global__ void __launch_bounds__(W2_BLOCK)
+grid_walk2_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__ pos_s,
+                  const float4 *__restrict__ vel_s, const uint32_t *__restrict__ cell_start,
+                  uint32_t n_all, float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
+                  unsigned *__restrict__ status, TapOut tap) {
+    __shared__ uint32_t list[W2_CAP][W2_BLOCK];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t s = blockIdx.x * W2_BLOCK + tid;
+    const bool active = s < n_all;
+    float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
+    Self self;
+    self.p = self.v = self.vhat = v3zero();
+    bool work = false;
+    int cx = 0, cy = 0, cz = 0;
+    if (active) {
+        pi4 = pos_s[s];
+        vi4 = vel_s[s];
+        self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
+        const bool ghost = __float_as_uint(vi4.w) != 0u;
+        work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
+        cx = cell_coord(pi4.x, g.origin[0], g.inv_cell, g.dim[0]);
+        cy = cell_coord(pi4.y, g.origin[1], g.inv_cell, g.dim[1]);
+        cz = cell_coord(pi4.z, g.origin[2], g.inv_cell, g.dim[2]);
+    }
+    V3 acc = v3zero();
+    int cnt = 0;
+
+    auto drain = [&]() {
+        int nb = 0;
+        for (int k = 0; k < cnt; ++k) {  // phase 2
+            const uint32_t j = list[k][tid];
+            const float4 pj = __ldg(pos_s + j);
+            V3 d;
+            const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
+            if (!pair_fov_culled(self, d, m2, P.cstar)) list[nb++][tid] = j;
         }
-        return;
-    }
-    const uint32_t idx = __float_as_uint(pi4.w);
-    if (TAP == TAP_NEIGHBORS) {
-        tap.nbr_count[idx] = n_count;
-        tap.nbr_hash[idx] = n_hash;
-        return;
-    }
-    Extras e;
-    unsigned flags = 0;
-    const V3 a = accel_total(P, self, acc, e, flags, TAP == TAP_ACCEL);
-    if (TAP == TAP_ACCEL) {
-        float *o = tap.accel3 + 3ull * idx;
-        o[0] = a.x; o[1] = a.y; o[2] = a.z;
-        if (tap.comp15) {
-            float *c = tap.comp15 + 15ull * idx;
-            c[0] = acc.x; c[1] = acc.y; c[2] = acc.z;
-            c[3] = e.lead.x; c[4] = e.lead.y; c[5] = e.lead.z;
-            c[6] = e.attr.x; c[7] = e.attr.y; c[8] = e.attr.z;
-            c[9] = e.bbox.x; c[10] = e.bbox.y; c[11] = e.bbox.z;
-            c[12] = e.steer.x; c[13] = e.steer.y; c[14] = e.steer.z;
+        for (int k = 0; k < nb; ++k) {  // phase 3
+            const uint32_t j = list[k][tid];
+            const float4 pj = __ldg(pos_s + j);
+            const float4 vj = __ldg(vel_s + j);
+            V3 d, contrib;
+            const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
+            if (pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar, contrib))
+                acc = vadd(acc, contrib);
         }
-        if (flags) atomicOr(status, flags);
-        return;
+        cnt = 0;
+    };
+
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+#pragma unroll 1
+    for (int dz = -1; dz <= 1; ++dz) {
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int z = cz + dz, y = cy + dy;
+            uint32_t jb = 0, je = 0;
+            if (work && z >= 0 && z < g.dim[2] && y >= 0 && y < g.dim[1]) {
+                const uint32_t rowbase = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
+                jb = __ldg(cell_start + rowbase + x0);
+                je = __ldg(cell_start + rowbase + x1 + 1);
+            }
+            const uint32_t nchunk = __reduce_max_sync(0xffffffffu, (je - jb + W2_CAP - 1) / W2_CAP);
+            for (uint32_t c = 0; c < nchunk; ++c) {
+                const uint32_t j0 = min(jb + c * W2_CAP, je), j1 = min(j0 + W2_CAP, je);
+                if (__any_sync(0xffffffffu, cnt + (int)(j1 - j0) > W2_CAP)) drain();
+#pragma unroll 4
+                for (uint32_t j = j0; j < j1; ++j) {  // phase 1
+                    const float4 pj = __ldg(pos_s + j);
+                    V3 d;
+                    const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
+                    if (!(m2 >= P.m2_cut)) list[cnt++][tid] = j;
+                }
+            }
+        }
     }
-    V3 np, nv;
-    euler(P, self.p, self.v, a, np, nv);
-    pos_out[s] = make_float4(np.x, np.y, np.z, pi4.w);
-    vel_out[s] = make_float4(nv.x, nv.y, nv.z, 0.0f);
-    if (flags) atomicOr(status, flags);
+    drain();
+    if (!active) return;
+    walk_finish<TAP>(P, s, pi4, vi4, self, acc, 0u, 0ull, pos_out, vel_out, status, tap);
 }
 
 int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap,
@@ -198,15 +252,36 @@ int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int
                      uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
                      const TapOut &tap_out, const uint8_t *) {
     if (!n_all) return FP_OK;
+    // FP_WALK_VARIANT (debug/tuning): 1 = one-phase, 2 = three-phase from global memory,
+    // 31.. = TMA-staged three-phase tile shapes (fp_walk.cu).  Default: staged.
+    static const int variant = [] {
+        const char *e = getenv("FP_WALK_VARIANT");
+        return e ? atoi(e) : 31;
+    }();
     const dim3 grid((n_all + WALK_BLOCK - 1) / WALK_BLOCK), block(WALK_BLOCK);
-    switch (tap) {
-        case TAP_STEP:
+    const dim3 grid2((n_all + W2_BLOCK - 1) / W2_BLOCK), block2(W2_BLOCK);
+    if ((tap == TAP_STEP || tap == TAP_ACCEL) && variant >= 30)
+        return launch_grid_walk3(st, P, g, tap, variant, pos_s, vel_s, cell_start, n_all, pos_out, vel_out,
+                                 status, tap_out);
+    if ((tap == TAP_STEP || tap == TAP_ACCEL) && variant == 1) {
+        if (tap == TAP_STEP)
             grid_walk_kernel<TAP_STEP><<<grid, block, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
                                                                pos_out, vel_out, status, tap_out);
-            break;
-        case TAP_ACCEL:
+        else
             grid_walk_kernel<TAP_ACCEL><<<grid, block, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
                                                                 pos_out, vel_out, status, tap_out);
+        count_launch();
+        FP_CUDA(cudaGetLastError());
+        return FP_OK;
+    }
+    switch (tap) {
+        case TAP_STEP:
+            grid_walk2_kernel<TAP_STEP><<<grid2, block2, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
+                                                                  pos_out, vel_out, status, tap_out);
+            break;
+        case TAP_ACCEL:
+            grid_walk2_kernel<TAP_ACCEL><<<grid2, block2, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
+                                                                   pos_out, vel_out, status, tap_out);
             break;
         case TAP_NEIGHBORS:
             grid_walk_kernel<TAP_NEIGHBORS><<<grid, block, 0, st>>>(P, g, pos_s, vel_s, cell_start,

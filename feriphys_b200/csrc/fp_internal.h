@@ -90,6 +90,12 @@ int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int
                      uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
                      const TapOut &tap_out, const uint8_t *owned_mask);
 
+// TMA-staged three-phase walk (fp_walk.cu); variant selects <BLOCK, TILE_CAP, CAP>
+int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, int variant,
+                      const float4 *pos_s, const float4 *vel_s, const uint32_t *cell_start,
+                      uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
+                      const TapOut &tap_out);
+
 // ---- misc kernels (fp_misc.cu) ----------------------------------------------
 int launch_aos6_to_soa(cudaStream_t st, const float *aos6, float4 *pos, float4 *vel, uint32_t n,
                        uint32_t first_index);

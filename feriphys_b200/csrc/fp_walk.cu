@@ -1,0 +1,316 @@
+// fp_walk.cu -- K3, production form: shared-memory staged 27-cell walk.
+//
+// A CTA owns BLOCK consecutive boids of the cell-sorted state (~BLOCK/8 cells
+// of one grid row).  For each of the nine (dy, dz) neighbour rows, everything
+// its threads can reach is ONE contiguous slot interval of the sorted position
+// array, so the CTA stages those nine intervals into shared memory with 1-D
+// TMA bulk copies (cp.async.bulk -> UBLKCP) signalled on an mbarrier: every
+// candidate position is fetched from L2/HBM once per CTA and then re-read ~24
+// times from shared memory.  Each thread then takes its own boid through three
+// warp-convergent phases:
+//   1. gate   -- every candidate: exact squared distance against m2_cut; the
+//                survivors' tile offsets (16 bit) go to a per-thread list in
+//                shared memory;
+//   2. FOV    -- survivors only: a cheap approximate cosine drops pairs that are
+//                CERTAINLY culled (margin 1e-5 >> its 1e-6 error bound); anything
+//                near the threshold is kept for the exact test of phase 3;
+//   3. forces -- remaining pairs: the exact pair function (pair_inrange, which
+//                re-tests the FOV exactly), accumulated in list (= slot) order.
+// A full list is drained (phases 2+3) before the next chunk, warp-uniformly, and
+// the row loop is kept rolled so the kernel stays inside the instruction cache.
+//
+// Arithmetic and summation order are exactly those of the one-phase kernel
+// (grid_walk_kernel): bit-identical to the reference loop (flocking.rs:133-151)
+// run over the same boids in cell-sorted order.  A boid's own slot is skipped:
+// for finite states its self-pair contributes exactly +0 (boid.rs:111,121,132).
+//
+// CTAs whose nine intervals exceed the tile (very dense clusters) take the
+// one-phase path straight from global memory -- slower, same result.
+#include "fp_grid.cuh"
+
+namespace fp {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int BLOCK, int TILE_CAP, int CAP>
+struct Walk3Smem {
+    float4 tpos[TILE_CAP];       // staged candidate positions (.w = caller index, unused here)
+    uint16_t list[CAP][BLOCK];   // per-thread survivor lists: tile offsets
+    uint32_t rng[10][BLOCK];     // per-thread (tile start | len << 16) per row; row 9 = final drain
+    uint32_t ub[9], ue[9];       // CTA-wide slot interval of each row
+    uint32_t toff[10];           // tile offset of each interval (prefix sum)
+    int fallback;
+    alignas(8) uint64_t bar;
+};
+
+// Conservative FOV pre-filter.  c~ is within 1e-6 of the exact cosine of boid.rs:102-105
+// (|vhat| = 1 +- 2e-7, rsqrt.approx and the fused dot are each good to a few ulp), so a
+// pair is dropped only when it is culled with a 1e-5 margin on both sides of the band
+// -1 <= c <= cstar; NaN never drops.  The exact test in pair_inrange has the last word.
+__device__ __forceinline__ bool fov_certainly_culled(const Self &s, V3 d, float m2, float cstar) {
+    const float q = fmaf(s.vhat.z, d.z, fmaf(s.vhat.y, d.y, s.vhat.x * d.x));
+    const float c = q * rsqrtf(m2);
+    return c < cstar - 1e-5f && c > -1.0f + 1e-5f;
+}
+
+template <int TAP, int BLOCK, int TILE_CAP, int CAP>
+__global__ void __launch_bounds__(BLOCK)
+grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__ pos_s,
+                  const float4 *__restrict__ vel_s, const uint32_t *__restrict__ cell_start,
+                  uint32_t n_all, float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
+                  unsigned *__restrict__ status, TapOut tap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using Smem = Walk3Smem<BLOCK, TILE_CAP, CAP>;
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t s = blockIdx.x * BLOCK + tid;
+    const bool active = s < n_all;
+
+    if (tid == 0) {
+        mbar_init(&S.bar, 1);
+        S.fallback = 0;
+    }
+    if (tid < 9) {
+        S.ub[tid] = 0xffffffffu;
+        S.ue[tid] = 0u;
+    }
+
+    float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
+    Self self;
+    self.p = self.v = self.vhat = v3zero();
+    bool work = false;
+    int cx = 0, cy = 0, cz = 0;
+    if (active) {
+        pi4 = pos_s[s];
+        vi4 = vel_s[s];
+        self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
+        const bool ghost = __float_as_uint(vi4.w) != 0u;
+        work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
+        cx = cell_coord(pi4.x, g.origin[0], g.inv_cell, g.dim[0]);
+        cy = cell_coord(pi4.y, g.origin[1], g.inv_cell, g.dim[1]);
+        cz = cell_coord(pi4.z, g.origin[2], g.inv_cell, g.dim[2]);
+    }
+    // the nine slot ranges of this boid, rows in ascending key order (dz outer, dy inner)
+    uint32_t jb[9], je[9];
+    {
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const int z = cz + r / 3 - 1, y = cy + r % 3 - 1;
+            jb[r] = je[r] = 0;
+            if (work && z >= 0 && z < g.dim[2] && y >= 0 && y < g.dim[1]) {
+                const uint32_t rowbase = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
+                jb[r] = __ldg(cell_start + rowbase + x0);
+                je[r] = __ldg(cell_start + rowbase + x1 + 1);
+            }
+        }
+    }
+    __syncthreads();  // barrier + ub/ue initialised
+    // CTA-wide union of each row's ranges: one contiguous interval per row
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        const bool has = je[r] > jb[r];
+        const uint32_t lo = __reduce_min_sync(0xffffffffu, has ? jb[r] : 0xffffffffu);
+        const uint32_t hi = __reduce_max_sync(0xffffffffu, has ? je[r] : 0u);
+        if ((tid & 31) == 0 && hi > 0) {
+            atomicMin(&S.ub[r], lo);
+            atomicMax(&S.ue[r], hi);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int r = 0; r < 9; ++r) {
+            S.toff[r] = total;
+            if (S.ue[r] > S.ub[r]) total += S.ue[r] - S.ub[r];
+            else S.ub[r] = S.ue[r] = 0;
+        }
+        S.toff[9] = total;
+        if (total > (uint32_t)TILE_CAP) {
+            S.fallback = 1;
+        } else if (total > 0) {
+            mbar_expect_tx(&S.bar, total * 16u);
+            for (int r = 0; r < 9; ++r) {
+                const uint32_t len = S.ue[r] - S.ub[r];
+                if (len) bulk_g2s(&S.tpos[S.toff[r]], pos_s + S.ub[r], len * 16u, &S.bar);
+            }
+        }
+    }
+    __syncthreads();
+    V3 acc = v3zero();
+    if (S.fallback) {
+        // one-phase walk from global memory (dense cluster: the tile would not fit)
+        if (work) {
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+            for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dim[2] - 1); ++z) {
+                for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+                    const uint32_t rowbase = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
+                    const uint32_t b = __ldg(cell_start + rowbase + x0);
+                    const uint32_t e = __ldg(cell_start + rowbase + x1 + 1);
+                    for (uint32_t j = b; j < e; ++j) {
+                        if (j == s) continue;
+                        const float4 pj = __ldg(pos_s + j);
+                        V3 d;
+                        const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
+                        if (m2 >= P.m2_cut) continue;
+                        const float4 vj = __ldg(vel_s + j);
+                        V3 contrib;
+                        if (pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar,
+                                                contrib))
+                            acc = vadd(acc, contrib);
+                    }
+                }
+            }
+        }
+    } else {
+        // per-thread ranges as (tile start | len << 16), so the row loop below stays rolled
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const uint32_t len = je[r] - jb[r];
+            const uint32_t t0 = len ? S.toff[r] + (jb[r] - S.ub[r]) : 0u;
+            S.rng[r][tid] = t0 | (len << 16);
+        }
+        S.rng[9][tid] = 0u;
+        // tile offset of this boid's own slot (row 4 = its own grid row); 0xffff if not staged
+        const uint32_t t_self = (work && je[4] > jb[4]) ? S.toff[4] + (s - S.ub[4]) : 0xffffu;
+        if (S.toff[9] > 0) mbar_wait(&S.bar, 0);
+        uint16_t *const lst = &S.list[0][tid];  // entry k at lst[k * BLOCK]
+        int cnt = 0;
+#pragma unroll 1
+        for (int r = 0; r <= 9; ++r) {
+            const uint32_t pk = S.rng[r][tid];
+            const uint32_t t0 = pk & 0xffffu, len = pk >> 16;
+            uint32_t i = 0;  // this lane's progress through its row range
+#pragma unroll 1
+            for (;;) {
+                // room every lane is guaranteed to have left in its list
+                int room = CAP - (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);
+                const bool more = __any_sync(0xffffffffu, i < len);
+                if (room == 0 || (r == 9 && room < CAP)) {
+                    int nb = 0;
+                    for (int k = 0; k < cnt; ++k) {  // phase 2: drop self and the certainly-culled
+                        const uint32_t t = lst[k * BLOCK];
+                        const float4 pj = S.tpos[t];
+                        const V3 d = v3(pj.x - self.p.x, pj.y - self.p.y, pj.z - self.p.z);
+                        const float m2 = fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x));
+                        if (t != t_self && !fov_certainly_culled(self, d, m2, P.cstar))
+                            lst[(nb++) * BLOCK] = (uint16_t)t;
+                    }
+                    // phase 3: exact forces in slot order.  The list ascends, so the row of an
+                    // entry (needed to turn its tile offset back into a slot for the velocity
+                    // gather) only moves forward; the next entry's velocity is prefetched.
+                    int row = 0;
+                    uint32_t row_end = S.toff[1], to_slot = S.ub[0] - S.toff[0];
+                    auto slot_of = [&](uint32_t t) {
+                        while (t >= row_end) {
+                            ++row;
+                            row_end = S.toff[row + 1];
+                            to_slot = S.ub[row] - S.toff[row];
+                        }
+                        return t + to_slot;
+                    };
+                    uint32_t t_nx = nb ? lst[0] : 0u;
+                    float4 v_nx = nb ? __ldg(vel_s + slot_of(t_nx)) : make_float4(0, 0, 0, 0);
+                    for (int k = 0; k < nb; ++k) {
+                        const uint32_t t = t_nx;
+                        const float4 vj = v_nx;
+                        if (k + 1 < nb) {
+                            t_nx = lst[(k + 1) * BLOCK];
+                            v_nx = __ldg(vel_s + slot_of(t_nx));
+                        }
+                        const float4 pj = S.tpos[t];
+                        V3 d, contrib;
+                        const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
+                        if (pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar,
+                                                contrib))
+                            acc = vadd(acc, contrib);
+                    }
+                    cnt = 0;
+                    room = CAP;
+                }
+                if (!more) break;
+                const uint32_t i1 = min(i + (uint32_t)room, len);
+                uint16_t *wp = lst + cnt * BLOCK;
+#pragma unroll 4
+                for (; i < i1; ++i) {  // phase 1: exact distance gate
+                    const float4 pj = S.tpos[t0 + i];
+                    V3 d;
+                    const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
+                    if (!(m2 >= P.m2_cut)) {
+                        *wp = (uint16_t)(t0 + i);
+                        wp += BLOCK;
+                    }
+                }
+                cnt = (int)(wp - lst) / BLOCK;
+            }
+        }
+    }
+    if (!active) return;
+    walk_finish<TAP>(P, s, pi4, vi4, self, acc, 0u, 0ull, pos_out, vel_out, status, tap);
+}
+
+template <int TAP, int BLOCK, int TILE_CAP, int CAP>
+static int launch3(cudaStream_t st, const DevParams &P, const GridDesc &g, const float4 *pos_s,
+                   const float4 *vel_s, const uint32_t *cell_start, uint32_t n_all, float4 *pos_out,
+                   float4 *vel_out, unsigned *status, const TapOut &tap_out) {
+    auto kern = grid_walk3_kernel<TAP, BLOCK, TILE_CAP, CAP>;
+    const int smem = (int)sizeof(Walk3Smem<BLOCK, TILE_CAP, CAP>);
+    FP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(n_all + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(P, g, pos_s, vel_s, cell_start, n_all, pos_out,
+                                                            vel_out, status, tap_out);
+    count_launch();
+    FP_CUDA(cudaGetLastError());
+    return FP_OK;
+}
+
+int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, int variant,
+                      const float4 *pos_s, const float4 *vel_s, const uint32_t *cell_start,
+                      uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
+                      const TapOut &tap_out) {
+#define FP_W3(B, T, C)                                                                               \
+    return tap == TAP_STEP                                                                           \
+               ? launch3<TAP_STEP, B, T, C>(st, P, g, pos_s, vel_s, cell_start, n_all, pos_out, vel_out, \
+                                            status, tap_out)                                         \
+               : launch3<TAP_ACCEL, B, T, C>(st, P, g, pos_s, vel_s, cell_start, n_all, pos_out,     \
+                                             vel_out, status, tap_out)
+    switch (variant) {
+        case 31: FP_W3(128, 2048, 64);   // 53 KB: 4 CTAs / SM
+        case 32: FP_W3(256, 3584, 64);   // 99 KB: 2 CTAs / SM
+        case 33: FP_W3(128, 1792, 48);   // 45 KB: 5 CTAs / SM
+        case 34: FP_W3(64, 1280, 64);    // 31 KB: 7 CTAs / SM
+        case 35: FP_W3(256, 3072, 48);   // 83 KB: 2 CTAs / SM
+        default: FP_W3(128, 2048, 64);
+    }
+#undef FP_W3
+}
+
+}  // namespace fp
