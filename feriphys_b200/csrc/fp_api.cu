@@ -8,6 +8,7 @@
 #include <new>
 
 #include "fp_internal.h"
+#include "fp_flock.h"
 #include "fp_shard.h"
 
 namespace fp {
@@ -98,40 +99,7 @@ void derive_params(const fp_config &c, DevParams &P) {
 
 using namespace fp;
 
-// ---- handle -------------------------------------------------------------------
-struct fp_flock {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    uint32_t n = 0;        // boids held by this handle (local rows when sharded)
-    uint32_t cap = 0;      // capacity of pos/vel
-    uint64_t n_global = 0;
-    uint32_t first_index = 0;
-    fp_config cfg{};
-    DevParams P{};
-    float4 *pos[2] = {nullptr, nullptr}, *vel[2] = {nullptr, nullptr};
-    int cur = 0;
-    bool permuted = false;
-    int method = FP_METHOD_AUTO, method_in_use = FP_METHOD_ALLPAIRS;
-    float *d_leads = nullptr, *d_attr = nullptr, *d_obs = nullptr, *d_lead_table = nullptr;
-    uint32_t n_leads = 0, n_attr = 0, n_obs = 0, table_rows = 0, table_leads = 0, table_cursor = 0;
-    unsigned *d_status = nullptr;
-    unsigned long long *d_census = nullptr;
-    float *d_bounds = nullptr;
-    // grid
-    GridDesc grid{};
-    bool grid_valid = false, domain_user = false;
-    float user_lo[3]{}, user_hi[3]{};
-    uint64_t steps_since_fit = 0;
-    GridWork work{};
-    // staging for host transfers
-    void *d_stage = nullptr;
-    size_t stage_bytes = 0;
-    // timing hook: three events per step (before sort phase, before influence, after)
-    std::vector<cudaEvent_t> ev_pool;
-    size_t ev_used = 0;
-    bool timing = false;
-    Shard *shard = nullptr;  // multi-GPU state (fp_shard.cu)
-};
+// struct fp_flock lives in fp_flock.h (shared with fp_shard.cu)
 
 namespace {
 
@@ -253,7 +221,10 @@ int fit_grid(fp_flock *f) {
     uint32_t bits = 1;
     while ((1ull << bits) < g.ncells) ++bits;
     g.key_bits = bits;
+    g.gdimx = g.dim[0];
+    g.xoff = 0;
     f->grid = g;
+    if (f->shard) return shard_grid_fitted(f->shard, f);  // slab layout + scratch are the shard's
 
     // scratch
     GridWork &w = f->work;
@@ -366,31 +337,10 @@ int run_tap(fp_flock *f, int tap, const TapOut &out) {
 
 }  // namespace
 
-// accessors used by fp_shard.cu
+// entry points fp_shard.cu needs from this file
 namespace fp {
-FlockView flock_view(fp_flock *f) {
-    FlockView v;
-    v.stream = f->stream;
-    v.P = &f->P;
-    v.pos[0] = f->pos[0]; v.pos[1] = f->pos[1];
-    v.vel[0] = f->vel[0]; v.vel[1] = f->vel[1];
-    v.cur = &f->cur;
-    v.n = &f->n;
-    v.cap = f->cap;
-    v.permuted = &f->permuted;
-    v.status = f->d_status;
-    v.grid = &f->grid;
-    v.work = &f->work;
-    v.first_index = f->first_index;
-    v.method = f->method;
-    v.cfg = &f->cfg;
-    return v;
-}
-int flock_grid_prepare_fit(fp_flock *f) {
-    if (!f->grid_valid || (!f->domain_user && f->steps_since_fit >= 256)) return fit_grid(f);
-    return FP_OK;
-}
-void flock_count_steps(fp_flock *f, uint64_t k) { f->steps_since_fit += k; }
+int flock_fit_grid(fp_flock *f) { return fit_grid(f); }
+void flock_select_leads(fp_flock *f) { select_leads(f); }
 }  // namespace fp
 
 // ---- C ABI ----------------------------------------------------------------------
@@ -929,31 +879,59 @@ int fp_state_rk4_combine(int device, size_t n, const float *s, const float *k1, 
 
 int fp_nccl_unique_id(uint8_t out128[128]) { return shard_unique_id(out128); }
 
+// host copy of the resident records; owned ones only (ghost / dead halo records are skipped)
+static int fetch_owned(fp_flock *f, std::vector<float4> &p, std::vector<float4> &v) {
+    p.resize(f->n);
+    v.resize(f->n);
+    if (f->n) {
+        FP_CUDA(cudaMemcpyAsync(p.data(), f->pos[f->cur], (size_t)f->n * sizeof(float4), cudaMemcpyDeviceToHost,
+                                f->stream));
+        FP_CUDA(cudaMemcpyAsync(v.data(), f->vel[f->cur], (size_t)f->n * sizeof(float4), cudaMemcpyDeviceToHost,
+                                f->stream));
+        FP_CUDA(cudaStreamSynchronize(f->stream));
+    }
+    size_t k = 0;
+    for (size_t i = 0; i < p.size(); ++i) {
+        uint32_t flag;
+        memcpy(&flag, &v[i].w, 4);
+        if (flag != 0) continue;
+        p[k] = p[i];
+        v[k] = v[i];
+        ++k;
+    }
+    p.resize(k);
+    v.resize(k);
+    return FP_OK;
+}
+
 int fp_flock_local_len(fp_flock *f, uint64_t *n_local) {
-    if (!f || !n_local) { set_error("null argument"); return FP_ERR_INVALID; }
-    *n_local = f->n;
+    int rc = check(f);
+    if (rc) return rc;
+    if (!n_local) { set_error("null argument"); return FP_ERR_INVALID; }
+    if (!f->shard) {
+        *n_local = f->n;
+        return FP_OK;
+    }
+    std::vector<float4> p, v;
+    if ((rc = fetch_owned(f, p, v))) return rc;
+    *n_local = p.size();
     return FP_OK;
 }
 
 int fp_flock_read_local(fp_flock *f, uint64_t *out_index, float *out_aos6) {
     int rc = check(f);
     if (rc) return rc;
-    if (!f->n) return FP_OK;
+    std::vector<float4> p, v;
+    if ((rc = fetch_owned(f, p, v))) return rc;
+    if (p.empty()) return FP_OK;
     if (!out_index || !out_aos6) { set_error("null output"); return FP_ERR_INVALID; }
-    const size_t bytes = (size_t)f->n * 6 * sizeof(float);
-    if ((rc = ensure_stage(f, bytes))) return rc;
-    if ((rc = launch_soa_to_aos6(f->stream, f->pos[f->cur], f->vel[f->cur], (float *)f->d_stage, f->n,
-                                 0, 0)))
-        return rc;
-    FP_CUDA(cudaMemcpyAsync(out_aos6, f->d_stage, bytes, cudaMemcpyDeviceToHost, f->stream));
-    std::vector<float4> p(f->n);
-    FP_CUDA(cudaMemcpyAsync(p.data(), f->pos[f->cur], (size_t)f->n * sizeof(float4), cudaMemcpyDeviceToHost,
-                            f->stream));
-    FP_CUDA(cudaStreamSynchronize(f->stream));
-    for (uint32_t i = 0; i < f->n; ++i) {
+    for (size_t i = 0; i < p.size(); ++i) {
         uint32_t u;
         memcpy(&u, &p[i].w, 4);
         out_index[i] = u;
+        float *o = out_aos6 + 6 * i;
+        o[0] = p[i].x; o[1] = p[i].y; o[2] = p[i].z;
+        o[3] = v[i].x; o[4] = v[i].y; o[5] = v[i].z;
     }
     return FP_OK;
 }

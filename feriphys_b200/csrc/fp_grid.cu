@@ -26,7 +26,7 @@ grid_keys_kernel(const GridDesc g, const float4 *__restrict__ pos, uint32_t n,
     uint32_t key = 0xffffffffu;
     if (valid) {
         const float4 p = pos[i];
-        const int cx = cell_coord(p.x, g.origin[0], g.inv_cell, g.dim[0]);
+        const int cx = cell_coord_x(g, p.x);
         const int cy = cell_coord(p.y, g.origin[1], g.inv_cell, g.dim[1]);
         const int cz = cell_coord(p.z, g.origin[2], g.inv_cell, g.dim[2]);
         key = (uint32_t)((cz * g.dim[1] + cy) * g.dim[0] + cx);
@@ -93,7 +93,7 @@ grid_walk_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__
         const bool ghost = __float_as_uint(vi4.w) != 0u;  // halo copy owned by another rank
         const bool need_pairs = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
         if (need_pairs) {
-            const int cx = cell_coord(pi4.x, g.origin[0], g.inv_cell, g.dim[0]);
+            const int cx = cell_coord_x(g, pi4.x);
             const int cy = cell_coord(pi4.y, g.origin[1], g.inv_cell, g.dim[1]);
             const int cz = cell_coord(pi4.z, g.origin[2], g.inv_cell, g.dim[2]);
             const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
@@ -188,7 +188,7 @@ grid_walk2_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
         self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
         const bool ghost = __float_as_uint(vi4.w) != 0u;
         work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
-        cx = cell_coord(pi4.x, g.origin[0], g.inv_cell, g.dim[0]);
+        cx = cell_coord_x(g, pi4.x);
         cy = cell_coord(pi4.y, g.origin[1], g.inv_cell, g.dim[1]);
         cz = cell_coord(pi4.z, g.origin[2], g.inv_cell, g.dim[2]);
     }

@@ -11,6 +11,14 @@ __device__ __forceinline__ int cell_coord(float x, float origin, float inv_cell,
     return min(max(c, 0), dim - 1);
 }
 
+// x coordinate: the GLOBAL cell layer (identical on every rank), shifted into this rank's
+// slab-local frame (layer 0 = left halo) and clamped to it.  Single GPU: xoff = 0,
+// gdimx = dim[0], i.e. plain cell_coord.
+__device__ __forceinline__ int cell_coord_x(const GridDesc &g, float x) {
+    const int c = cell_coord(x, g.origin[0], g.inv_cell, g.gdimx) - g.xoff;
+    return min(max(c, 0), g.dim[0] - 1);
+}
+
 // Shared epilogue of the walk kernels: per-boid extras (flocking.rs:105-113), Euler
 // update (flocking.rs:116-117) and the debug taps.
 template <int TAP>

@@ -47,9 +47,11 @@ struct GridDesc {
     float origin[3];
     float inv_cell;
     float cell;
-    int dim[3];
-    uint32_t ncells;
-    uint32_t key_bits;
+    int dim[3];        // cells of THIS rank's grid (slab + one halo layer each side when sharded)
+    uint32_t ncells;   // dim[0] * dim[1] * dim[2]
+    uint32_t key_bits; // bits of ncells (the value ncells itself is the "dead record" key)
+    int gdimx;         // global cell layers along x (== dim[0] on a single GPU)
+    int xoff;          // global layer index of local layer 0 (0 on a single GPU)
 };
 
 // ---- all-pairs (fp_allpairs.cu) --------------------------------------------

@@ -115,7 +115,7 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
         self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
         const bool ghost = __float_as_uint(vi4.w) != 0u;
         work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
-        cx = cell_coord(pi4.x, g.origin[0], g.inv_cell, g.dim[0]);
+        cx = cell_coord_x(g, pi4.x);
         cy = cell_coord(pi4.y, g.origin[1], g.inv_cell, g.dim[1]);
         cz = cell_coord(pi4.z, g.origin[2], g.inv_cell, g.dim[2]);
     }

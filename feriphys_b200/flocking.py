@@ -214,13 +214,17 @@ class Simulation:
         self.obstacles = obstacles
         self.attractors = attractors
         state = f32c(_state, (-1, 6))
+        self._h = self._create(state, device)
+        check(self._lib.fp_flock_set_method(self._h, method))
+        self._push_tables()
+
+    def _create(self, state: np.ndarray, device: int):
+        """-> library handle; sets ``self._n`` (rows of the per-boid outputs)."""
         self._n = len(state)
         h = C.c_void_p()
         cfg = self.config.to_c()
         check(self._lib.fp_flock_create(C.byref(h), C.byref(cfg), self._n, ptr(state), device))
-        self._h = h
-        check(self._lib.fp_flock_set_method(self._h, method))
-        self._push_tables()
+        return h
 
     new = classmethod(lambda cls, *a, **k: cls(*a, **k))
 

@@ -57,6 +57,10 @@ enum {
 /* Status bits (fp_flock_status): raised where the reference would panic. */
 #define FP_STATUS_STEER_NEGATIVE 1u /* Duration::from_secs_f32(negative), obstacle.rs:25 */
 #define FP_STATUS_STEER_NAN_OVF 2u  /* Duration::from_secs_f32(NaN / overflow) */
+/* Sharded (multi-GPU) grid runs only; any of these means the step was NOT exact: */
+#define FP_STATUS_SLAB_CAPACITY 4u  /* a rank's slab outgrew its buffers */
+#define FP_STATUS_HALO_OVERFLOW 8u  /* a face message outgrew the halo buffer */
+#define FP_STATUS_SLAB_JUMP 16u     /* a boid crossed more than one cell layer in one step */
 
 typedef struct fp_flock fp_flock; /* opaque; owns all device memory */
 
