@@ -462,9 +462,8 @@ def main():
     n = args.n or WORLDS_N(args.workload)
     first, count = 0, None
     if world > 1 and args.impl == "ours":
-        per = n // world
-        first = rank * per
-        count = per if rank < world - 1 else n - first
+        from feriphys_b200.sharded import shard_range
+        first, count = shard_range(n, rank, world)
     w = build_workload(args.workload, args.n, first, count)
     w["first"] = first
     w["method_resolved"] = args.method or w["method"]
