@@ -386,12 +386,7 @@ def run_ours(args, w, rank, world, local_rank):
     steps_seen = max(1, nst)
     grid = w["method_resolved"] == "grid"
     in_range, candidates = pairs_per_boid_step(census, n)
-    if world > 1 and dist is not None:
-        cc = torch.tensor([in_range, candidates, float(census[0]), float(census[1]), float(census[2])],
-                          device="cuda", dtype=torch.float64)
-        dist.all_reduce(cc)
-        in_range, candidates = float(cc[0]), float(cc[1])
-        census = np.array([cc[2].item(), cc[3].item(), cc[4].item(), cc[1].item()])
+    # (on a sharded flock fp_flock_pair_census already returns the all-rank totals)
     flops_step = 8.0 * float(census[0]) + 18.0 * float(census[1]) + 54.0 * float(census[2])
     infl_s = infl_ms / 1e3 / steps_seen if w["method_resolved"] != "small" else dev_s / K
     n_local = n / world
