@@ -81,6 +81,7 @@ _PROTOS = {
                                           C.c_uint64, _P, C.c_int, C.c_int, C.c_int, _P]),
     "fp_flock_local_len": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "fp_flock_read_local": (C.c_int, [_P, _P, _P]),
+    "fp_debug_fastmath_check": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _P]),
     "fp_last_error": (C.c_char_p, []),
     "fp_version": (C.c_char_p, []),
     "fp_launch_count": (C.c_uint64, []),

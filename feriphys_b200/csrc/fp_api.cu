@@ -93,6 +93,14 @@ void derive_params(const fp_config &c, DevParams &P) {
     P.steer_secs = c.time_to_start_steering_secs;
     P.steer_nanos = c.time_to_start_steering_nanos;
     P.steering_overrides = c.steering_overrides ? 1 : 0;
+    // branch-free exact path: every scalar a normal number of moderate exponent
+    auto moderate = [](float x) { return std::isfinite(x) && fabsf(x) >= 0x1p-40f && fabsf(x) <= 0x1p40f; };
+    auto bounded = [](float x) { return std::isfinite(x) && fabsf(x) <= 0x1p40f; };
+    P.fast_ok = moderate(P.neg_f_a) && moderate(P.fall) && P.fall > 0.0f && bounded(P.thr) && bounded(P.f_c) &&
+                bounded(P.f_v);
+    int e = 0;
+    P.fall_pow2 = P.fast_ok && frexpf(P.fall, &e) == 0.5f;
+    P.inv_fall = P.fall_pow2 ? 1.0f / P.fall : 0.0f;
 }
 
 }  // namespace fp
@@ -878,6 +886,17 @@ int fp_state_rk4_combine(int device, size_t n, const float *s, const float *k1, 
 }
 
 int fp_nccl_unique_id(uint8_t out128[128]) { return shard_unique_id(out128); }
+
+int fp_debug_fastmath_check(int device, uint64_t n, uint64_t seed, uint64_t out_mismatch[2]) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        set_error("no usable CUDA device -- this library has no CPU fallback");
+        return FP_ERR_CUDA;
+    }
+    if (!out_mismatch) { set_error("null output"); return FP_ERR_INVALID; }
+    FP_CUDA(cudaSetDevice(device));
+    return launch_fastmath_check(n, seed, out_mismatch);
+}
 
 // host copy of the resident records; owned ones only (ghost / dead halo records are skipped)
 static int fetch_owned(fp_flock *f, std::vector<float4> &p, std::vector<float4> &v) {

@@ -115,6 +115,7 @@ int launch_state_combine_rk4(cudaStream_t st, const float *s, const float *k1, c
 // State<boid>::euler_step / rk4_step with frozen acceleration: accel3 by internal order
 int launch_flock_state_step(cudaStream_t st, float4 *pos, float4 *vel, const float *accel3_by_index,
                             uint32_t n, uint32_t first_index, float h, int rk4);
+int launch_fastmath_check(uint64_t n, uint64_t seed, uint64_t out_mismatch[2]);
 int launch_bounds(cudaStream_t st, const float4 *pos, uint32_t n, float *out6 /*device*/);
 int launch_fill_u32(cudaStream_t st, uint32_t *p, uint32_t v, size_t n);
 // generic exclusive scan in place over n uint32 (n <= 2^28); tmp >= (n/4096 + 2) elements

@@ -268,6 +268,57 @@ int launch_bounds(cudaStream_t st, const float4 *pos, uint32_t n, float *out6) {
     return FP_OK;
 }
 
+// ---- self-test of the branch-free exact sqrt / division (fp_device.cuh) ------------------
+__global__ void fastmath_check_kernel(uint64_t n, uint64_t seed, unsigned long long *out) {
+    unsigned long long bad_sqrt = 0, bad_div = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long r0 = mix64(seed + 3 * i), r1 = mix64(seed + 3 * i + 1),
+                                 r2 = mix64(seed + 3 * i + 2);
+        // random mantissas, exponents drawn from the admitted ranges
+        auto make = [](unsigned long long r, int elo, int ehi, bool neg) {
+            const unsigned mant = (unsigned)(r & 0x7fffffu);
+            const int e = elo + (int)((r >> 23) % (unsigned)(ehi - elo + 1));
+            const unsigned sign = neg ? (unsigned)((r >> 60) & 1u) << 31 : 0u;
+            return __uint_as_float(sign | ((unsigned)(e + 127) << 23) | mant);
+        };
+        const float x = make(r0, -60, 60, false);  // m2
+        if (__float_as_uint(sqrt_rn_fast(x)) != __float_as_uint(__fsqrt_rn(x))) ++bad_sqrt;
+        const float mag = __fsqrt_rn(x);           // in 2^+-30
+        const float a = make(r1, -40, 40, true);   // neg_f_a-like numerators
+        const float b = make(r2, -40, 40, false);  // fall-like divisors
+        const float m = fmul(mag, mag);
+        const float num = make(r1 >> 7, -53, 41, true);
+        if (__float_as_uint(div_rn_fast(1.0f, mag)) != __float_as_uint(__fdiv_rn(1.0f, mag))) ++bad_div;
+        if (__float_as_uint(div_rn_fast(a, m)) != __float_as_uint(__fdiv_rn(a, m))) ++bad_div;
+        if (__float_as_uint(div_rn_fast(num, b)) != __float_as_uint(__fdiv_rn(num, b))) ++bad_div;
+        // the everyday range: distances of 1e-3 .. 1e3
+        const float xe = make(r2 >> 9, -20, 20, false);
+        const float me = __fsqrt_rn(xe);
+        if (__float_as_uint(sqrt_rn_fast(xe)) != __float_as_uint(me)) ++bad_sqrt;
+        if (__float_as_uint(div_rn_fast(1.0f, me)) != __float_as_uint(__fdiv_rn(1.0f, me))) ++bad_div;
+        if (__float_as_uint(div_rn_fast(-1.0f, fmul(me, me))) != __float_as_uint(__fdiv_rn(-1.0f, fmul(me, me))))
+            ++bad_div;
+    }
+    if (bad_sqrt) atomicAdd(out, bad_sqrt);
+    if (bad_div) atomicAdd(out + 1, bad_div);
+}
+
+int launch_fastmath_check(uint64_t n, uint64_t seed, uint64_t out_mismatch[2]) {
+    unsigned long long *d = nullptr;
+    FP_CUDA(cudaMalloc((void **)&d, 2 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemset(d, 0, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        fastmath_check_kernel<<<148 * 8, 256>>>(n, seed, d);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_mismatch, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "fastmath check", __FILE__, __LINE__);
+    return FP_OK;
+}
+
 __global__ void fill_u32_kernel(uint32_t *p, uint32_t v, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

@@ -82,7 +82,7 @@ __device__ __forceinline__ bool fov_certainly_culled(const Self &s, V3 d, float 
     return c < cstar - 1e-5f && c > -1.0f + 1e-5f;
 }
 
-template <int TAP, int BLOCK, int TILE_CAP, int CAP>
+template <int TAP, int BLOCK, int TILE_CAP, int CAP, int PH>
 __global__ void __launch_bounds__(BLOCK)
 grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__ pos_s,
                   const float4 *__restrict__ vel_s, const uint32_t *__restrict__ cell_start,
@@ -216,14 +216,28 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                 int room = CAP - (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);
                 const bool more = __any_sync(0xffffffffu, i < len);
                 if (room == 0 || (r == 9 && room < CAP)) {
+                    // phase 2: drop self and the certainly-culled.  Batches of PH: all list and
+                    // tile loads of a batch are issued before its stores (the compiler must
+                    // assume the 16-bit list stores alias the tile), compaction stays in order.
                     int nb = 0;
-                    for (int k = 0; k < cnt; ++k) {  // phase 2: drop self and the certainly-culled
-                        const uint32_t t = lst[k * BLOCK];
-                        const float4 pj = S.tpos[t];
-                        const V3 d = v3(pj.x - self.p.x, pj.y - self.p.y, pj.z - self.p.z);
-                        const float m2 = fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x));
-                        if (t != t_self && !fov_certainly_culled(self, d, m2, P.cstar))
-                            lst[(nb++) * BLOCK] = (uint16_t)t;
+                    for (int k = 0; k < cnt; k += PH) {
+                        uint32_t tt[PH];
+                        float4 pp[PH];
+#pragma unroll
+                        for (int u = 0; u < PH; ++u) tt[u] = lst[min(k + u, cnt - 1) * BLOCK];
+#pragma unroll
+                        for (int u = 0; u < PH; ++u) pp[u] = S.tpos[tt[u]];
+                        bool keep[PH];
+#pragma unroll
+                        for (int u = 0; u < PH; ++u) {
+                            const V3 d = v3(pp[u].x - self.p.x, pp[u].y - self.p.y, pp[u].z - self.p.z);
+                            const float m2 = fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x));
+                            keep[u] = k + u < cnt && tt[u] != t_self &&
+                                      !fov_certainly_culled(self, d, m2, P.cstar);
+                        }
+#pragma unroll
+                        for (int u = 0; u < PH; ++u)
+                            if (keep[u]) lst[(nb++) * BLOCK] = (uint16_t)tt[u];
                     }
                     // phase 3: exact forces in slot order.  The list ascends, so the row of an
                     // entry (needed to turn its tile offset back into a slot for the velocity
@@ -238,21 +252,44 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                         }
                         return t + to_slot;
                     };
+                    // Two entries per trip: their (branch-free) force evaluations are independent
+                    // and interleave; the two adds into acc stay in list order.
                     uint32_t t_nx = nb ? lst[0] : 0u;
                     float4 v_nx = nb ? __ldg(vel_s + slot_of(t_nx)) : make_float4(0, 0, 0, 0);
-                    for (int k = 0; k < nb; ++k) {
-                        const uint32_t t = t_nx;
-                        const float4 vj = v_nx;
-                        if (k + 1 < nb) {
-                            t_nx = lst[(k + 1) * BLOCK];
+                    for (int k = 0; k < nb; k += 2) {
+                        const uint32_t ta = t_nx;
+                        const float4 va = v_nx;
+                        const bool hasb = k + 1 < nb;
+                        uint32_t tb = ta;
+                        float4 vb = va;
+                        if (hasb) {
+                            tb = lst[(k + 1) * BLOCK];
+                            vb = __ldg(vel_s + slot_of(tb));
+                        }
+                        if (k + 2 < nb) {
+                            t_nx = lst[(k + 2) * BLOCK];
                             v_nx = __ldg(vel_s + slot_of(t_nx));
                         }
-                        const float4 pj = S.tpos[t];
-                        V3 d, contrib;
-                        const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
-                        if (pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar,
-                                                contrib))
-                            acc = vadd(acc, contrib);
+                        const float4 pa = S.tpos[ta], pb = S.tpos[tb];
+                        V3 da, db;
+                        const float ma = pair_m2(self, v3(pa.x, pa.y, pa.z), da);
+                        const float mb = pair_m2(self, v3(pb.x, pb.y, pb.z), db);
+                        const bool fast = P.fast_ok && ma >= FAST_M2_LO && ma <= FAST_M2_HI &&
+                                          mb >= FAST_M2_LO && mb <= FAST_M2_HI;
+                        if (fast) {
+                            bool visa, visb;
+                            const V3 fa = pair_force_fast(P, self, da, ma, v3(va.x, va.y, va.z), visa);
+                            const V3 fb = pair_force_fast(P, self, db, mb, v3(vb.x, vb.y, vb.z), visb);
+                            if (visa) acc = vadd(acc, fa);
+                            if (hasb && visb) acc = vadd(acc, fb);
+                        } else {  // extreme distances (coincident boids, ...): generic exact path
+                            V3 contrib;
+                            if (pair_inrange<false>(P, self, da, ma, v3(va.x, va.y, va.z), 1.0f, P.cstar, contrib))
+                                acc = vadd(acc, contrib);
+                            if (hasb &&
+                                pair_inrange<false>(P, self, db, mb, v3(vb.x, vb.y, vb.z), 1.0f, P.cstar, contrib))
+                                acc = vadd(acc, contrib);
+                        }
                     }
                     cnt = 0;
                     room = CAP;
@@ -260,16 +297,27 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                 if (!more) break;
                 const uint32_t i1 = min(i + (uint32_t)room, len);
                 uint16_t *wp = lst + cnt * BLOCK;
-#pragma unroll 4
-                for (; i < i1; ++i) {  // phase 1: exact distance gate
-                    const float4 pj = S.tpos[t0 + i];
-                    V3 d;
-                    const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
-                    if (!(m2 >= P.m2_cut)) {
-                        *wp = (uint16_t)(t0 + i);
-                        wp += BLOCK;
+                // phase 1: exact distance gate, PH candidates per batch with the tile loads
+                // issued ahead of the list stores; the tail re-reads the last candidate, masked
+                for (; i < i1; i += PH) {
+                    const uint32_t tb = t0 + i, rem = i1 - i;
+                    float4 pp[PH];
+#pragma unroll
+                    for (int u = 0; u < PH; ++u) pp[u] = S.tpos[tb + min((uint32_t)u, rem - 1)];
+                    float mm[PH];
+#pragma unroll
+                    for (int u = 0; u < PH; ++u) {
+                        V3 d;
+                        mm[u] = pair_m2(self, v3(pp[u].x, pp[u].y, pp[u].z), d);
                     }
+#pragma unroll
+                    for (int u = 0; u < PH; ++u)
+                        if ((uint32_t)u < rem && !(mm[u] >= P.m2_cut)) {
+                            *wp = (uint16_t)(tb + u);
+                            wp += BLOCK;
+                        }
                 }
+                i = i1;
                 cnt = (int)(wp - lst) / BLOCK;
             }
         }
@@ -278,11 +326,11 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
     walk_finish<TAP>(P, s, pi4, vi4, self, acc, 0u, 0ull, pos_out, vel_out, status, tap);
 }
 
-template <int TAP, int BLOCK, int TILE_CAP, int CAP>
+template <int TAP, int BLOCK, int TILE_CAP, int CAP, int PH>
 static int launch3(cudaStream_t st, const DevParams &P, const GridDesc &g, const float4 *pos_s,
                    const float4 *vel_s, const uint32_t *cell_start, uint32_t n_all, float4 *pos_out,
                    float4 *vel_out, unsigned *status, const TapOut &tap_out) {
-    auto kern = grid_walk3_kernel<TAP, BLOCK, TILE_CAP, CAP>;
+    auto kern = grid_walk3_kernel<TAP, BLOCK, TILE_CAP, CAP, PH>;
     const int smem = (int)sizeof(Walk3Smem<BLOCK, TILE_CAP, CAP>);
     FP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<(n_all + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(P, g, pos_s, vel_s, cell_start, n_all, pos_out,
@@ -296,19 +344,20 @@ int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, in
                       const float4 *pos_s, const float4 *vel_s, const uint32_t *cell_start,
                       uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
                       const TapOut &tap_out) {
-#define FP_W3(B, T, C)                                                                               \
+#define FP_W3(B, T, C, H)                                                                              \
     return tap == TAP_STEP                                                                           \
-               ? launch3<TAP_STEP, B, T, C>(st, P, g, pos_s, vel_s, cell_start, n_all, pos_out, vel_out, \
+               ? launch3<TAP_STEP, B, T, C, H>(st, P, g, pos_s, vel_s, cell_start, n_all, pos_out, vel_out, \
                                             status, tap_out)                                         \
-               : launch3<TAP_ACCEL, B, T, C>(st, P, g, pos_s, vel_s, cell_start, n_all, pos_out,     \
+               : launch3<TAP_ACCEL, B, T, C, H>(st, P, g, pos_s, vel_s, cell_start, n_all, pos_out,     \
                                              vel_out, status, tap_out)
     switch (variant) {
-        case 31: FP_W3(128, 2048, 64);   // 53 KB: 4 CTAs / SM
-        case 32: FP_W3(256, 3584, 64);   // 99 KB: 2 CTAs / SM
-        case 33: FP_W3(128, 1792, 48);   // 45 KB: 5 CTAs / SM
-        case 34: FP_W3(64, 1280, 64);    // 31 KB: 7 CTAs / SM
-        case 35: FP_W3(256, 3072, 48);   // 83 KB: 2 CTAs / SM
-        default: FP_W3(128, 2048, 64);
+        case 31: FP_W3(128, 2048, 64, 4);   // 53 KB: 4 CTAs / SM
+        case 32: FP_W3(128, 2048, 64, 8);
+        case 33: FP_W3(256, 3584, 64, 4);   // 99 KB: 2 CTAs / SM
+        case 34: FP_W3(256, 3584, 64, 8);
+        case 35: FP_W3(64, 1280, 64, 4);    // 31 KB: 7 CTAs / SM
+        case 36: FP_W3(128, 2048, 64, 2);
+        default: FP_W3(128, 2048, 64, 4);
     }
 #undef FP_W3
 }

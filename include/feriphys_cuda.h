@@ -178,6 +178,11 @@ int fp_flock_local_len(fp_flock *f, uint64_t *n_local);
 /* Local state with global indices: out_index n_local x u64, out_aos6 n_local x 6. */
 int fp_flock_read_local(fp_flock *f, uint64_t *out_index, float *out_aos6);
 
+/* Self-test (ADDITION): compares the branch-free sqrt / division sequences of the grid walk
+ * with __fsqrt_rn / __fdiv_rn bit for bit on n pseudo-random operand sets drawn from the
+ * exponent ranges the kernel admits; out_mismatch = {sqrt mismatches, div mismatches}. */
+int fp_debug_fastmath_check(int device, uint64_t n, uint64_t seed, uint64_t out_mismatch[2]);
+
 const char *fp_last_error(void);
 /* "feriphys-cuda <version> sm_100a" */
 const char *fp_version(void);

@@ -74,6 +74,7 @@ extern "C" {
                                    rank: c_int, world: c_int, nccl_unique_id: *const u8) -> c_int;
     pub fn fp_flock_local_len(f: *mut fp_flock, n_local: *mut u64) -> c_int;
     pub fn fp_flock_read_local(f: *mut fp_flock, out_index: *mut u64, out_aos6: *mut f32) -> c_int;
+    pub fn fp_debug_fastmath_check(device: c_int, n: u64, seed: u64, out_mismatch: *mut u64) -> c_int;
     pub fn fp_last_error() -> *const c_char;
     pub fn fp_version() -> *const c_char;
     pub fn fp_launch_count() -> u64;
