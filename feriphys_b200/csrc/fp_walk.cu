@@ -63,7 +63,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 template <int BLOCK, int TILE_CAP, int CAP>
 struct Walk3Smem {
-    float4 tpos[TILE_CAP];       // staged candidate positions (.w = caller index, unused here)
+    float4 tpos[TILE_CAP + 8];   // staged candidate positions (+ padding for masked tail reads)
     uint16_t list[CAP][BLOCK];   // per-thread survivor lists: tile offsets
     uint32_t rng[10][BLOCK];     // per-thread (tile start | len << 16) per row; row 9 = final drain
     uint32_t ub[9], ue[9];       // CTA-wide slot interval of each row
@@ -296,14 +296,14 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                 }
                 if (!more) break;
                 const uint32_t i1 = min(i + (uint32_t)room, len);
-                uint16_t *wp = lst + cnt * BLOCK;
-                // phase 1: exact distance gate, PH candidates per batch with the tile loads
-                // issued ahead of the list stores; the tail re-reads the last candidate, masked
-                for (; i < i1; i += PH) {
-                    const uint32_t tb = t0 + i, rem = i1 - i;
+                // phase 1: exact distance gate.  PH candidates per batch, all tile loads issued
+                // ahead of the list stores; full batches carry no tail logic, and the (masked)
+                // tail may read up to PH-1 records past its range -- the tile is padded for that.
+                uint32_t w = (uint32_t)cnt * BLOCK;  // list cursor, in entries
+                auto gate = [&](uint32_t tb, uint32_t live) {
                     float4 pp[PH];
 #pragma unroll
-                    for (int u = 0; u < PH; ++u) pp[u] = S.tpos[tb + min((uint32_t)u, rem - 1)];
+                    for (int u = 0; u < PH; ++u) pp[u] = S.tpos[tb + u];
                     float mm[PH];
 #pragma unroll
                     for (int u = 0; u < PH; ++u) {
@@ -312,13 +312,15 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                     }
 #pragma unroll
                     for (int u = 0; u < PH; ++u)
-                        if ((uint32_t)u < rem && !(mm[u] >= P.m2_cut)) {
-                            *wp = (uint16_t)(tb + u);
-                            wp += BLOCK;
+                        if ((uint32_t)u < live && !(mm[u] >= P.m2_cut)) {
+                            lst[w] = (uint16_t)(tb + u);
+                            w += BLOCK;
                         }
-                }
+                };
+                for (; i + PH <= i1; i += PH) gate(t0 + i, PH);
+                if (i < i1) gate(t0 + i, i1 - i);
                 i = i1;
-                cnt = (int)(wp - lst) / BLOCK;
+                cnt = (int)(w / BLOCK);
             }
         }
     }
