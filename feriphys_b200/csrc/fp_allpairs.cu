@@ -57,8 +57,7 @@ allpairs_kernel(const DevParams P, const float4 *__restrict__ pos_all,
                         if (m2 >= P.m2_cut) continue;
                         const float4 vj = sv[jj];
                         V3 contrib;
-                        if (pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar,
-                                                contrib))
+                        if (pair_flock(P, self, d, m2, v3(vj.x, vj.y, vj.z), contrib))
                             acc = vadd(acc, contrib);
                     } else {
                         const float4 vj = sv[jj];

@@ -110,8 +110,7 @@ grid_walk_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__
                             if (m2 >= P.m2_cut) continue;
                             const float4 vj = __ldg(vel_s + j);
                             V3 contrib;
-                            if (pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar,
-                                                    contrib))
+                            if (pair_flock(P, self, d, m2, v3(vj.x, vj.y, vj.z), contrib))
                                 acc = vadd(acc, contrib);
                         } else {
                             const float4 vj = __ldg(vel_s + j);
@@ -210,7 +209,7 @@ grid_walk2_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
             const float4 vj = __ldg(vel_s + j);
             V3 d, contrib;
             const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
-            if (pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar, contrib))
+            if (pair_flock(P, self, d, m2, v3(vj.x, vj.y, vj.z), contrib))
                 acc = vadd(acc, contrib);
         }
         cnt = 0;

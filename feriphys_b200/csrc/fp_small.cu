@@ -62,7 +62,7 @@ small_kernel(DevParams P, float4 *__restrict__ gpos, float4 *__restrict__ gvel, 
                     if (!(m2 >= P.m2_cut)) {
                         const float4 vj = S.vel[cur][j];
                         V3 t;
-                        if (pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar, t)) c = t;
+                        if (pair_flock(P, self, d, m2, v3(vj.x, vj.y, vj.z), t)) c = t;
                     }
                     S.contrib[wid][0][j] = c.x;
                     S.contrib[wid][1][j] = c.y;

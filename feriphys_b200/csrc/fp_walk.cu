@@ -184,8 +184,7 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                         if (m2 >= P.m2_cut) continue;
                         const float4 vj = __ldg(vel_s + j);
                         V3 contrib;
-                        if (pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar,
-                                                contrib))
+                        if (pair_flock(P, self, d, m2, v3(vj.x, vj.y, vj.z), contrib))
                             acc = vadd(acc, contrib);
                     }
                 }
