@@ -379,8 +379,36 @@ def run_ours(args, w, rank, world, local_rank):
         e2e = {"value": n * ke / te, "unit": "boid-steps/s", "h2d_bytes_per_step": int(n * 24),
                "d2h_bytes_per_step": int(n * 24), "steps": ke,
                "path": "fp_flock_write_state -> fp_flock_step -> fp_flock_read_state, pinned host buffers"}
-    elif world > 1:
-        e2e = sim.e2e(K, barrier) if hasattr(sim, "e2e") else None
+        # the reference's own per-frame call sequence (demos/flocking.rs:215-227): step(), then
+        # get_boid_instances(); the state stays where Simulation keeps it
+        inst = torch.empty((n, 8), dtype=torch.float32).pin_memory().numpy()
+        _lib.check(lib.fp_flock_read_instances(sim._h, _lib.ptr(inst)))
+        barrier()
+        tf = time.perf_counter()
+        for _ in range(ke):
+            sim.step()
+            _lib.check(lib.fp_flock_read_instances(sim._h, _lib.ptr(inst)))
+        barrier()
+        tf = time.perf_counter() - tf
+        e2e["frame"] = {"value": n * ke / tf, "unit": "boid-steps/s", "d2h_bytes_per_step": int(n * 32),
+                        "h2d_bytes_per_step": int(28 * len(sim.lead_boids or [])),
+                        "path": "Simulation.step() -> get_boid_instances() each step (lead rows up, instances down)"}
+    elif not args.no_e2e:
+        # sharded: every rank steps and reads back the boids it owns
+        sim.step_many(1); sim.read_local()
+        ke = max(1, min(K, 10))
+        barrier()
+        te = time.perf_counter()
+        for _ in range(ke):
+            sim.step_many(1)
+            idx_l, st_l = sim.read_local()
+        barrier()
+        te = time.perf_counter() - te
+        tt = torch.tensor([te], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * ke / float(tt[0]), "unit": "boid-steps/s", "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": int(n * 32), "steps": ke,
+               "path": "fp_flock_step -> fp_flock_read_local on every rank (each rank reads the boids it owns)"}
 
     hbm, sm_max, peak_src = measured_peaks()
     steps_seen = max(1, nst)
