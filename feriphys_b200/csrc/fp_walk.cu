@@ -68,9 +68,14 @@ struct Walk3Smem {
     uint32_t rng[10][BLOCK];     // per-thread (tile start | len << 16) per row; row 9 = final drain
     uint32_t ub[9], ue[9];       // CTA-wide slot interval of each row
     uint32_t toff[10];           // tile offset of each interval (prefix sum)
+    uint32_t tslot[9];           // slot - tile offset within each interval (ub[r] - toff[r])
     int fallback;
     alignas(8) uint64_t bar;
 };
+
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // Conservative FOV pre-filter.  c~ is within 1e-6 of the exact cosine of boid.rs:102-105
 // (|vhat| = 1 +- 2e-7, rsqrt.approx and the fused dot are each good to a few ulp), so a
@@ -88,6 +93,7 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                   const float4 *__restrict__ vel_s, const uint32_t *__restrict__ cell_start,
                   uint32_t n_all, float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
                   unsigned *__restrict__ status, TapOut tap) {
+    static_assert(TILE_CAP + 8 <= 4096, "list entries carry a 12-bit tile offset");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = Walk3Smem<BLOCK, TILE_CAP, CAP>;
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -155,6 +161,7 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
             else S.ub[r] = S.ue[r] = 0;
         }
         S.toff[9] = total;
+        for (int r = 0; r < 9; ++r) S.tslot[r] = S.ub[r] - S.toff[r];
         if (total > (uint32_t)TILE_CAP) {
             S.fallback = 1;
         } else if (total > 0) {
@@ -225,32 +232,25 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
 #pragma unroll
                         for (int u = 0; u < PH; ++u) tt[u] = lst[min(k + u, cnt - 1) * BLOCK];
 #pragma unroll
-                        for (int u = 0; u < PH; ++u) pp[u] = S.tpos[tt[u]];
+                        for (int u = 0; u < PH; ++u) pp[u] = S.tpos[tt[u] & 0xfffu];
                         bool keep[PH];
 #pragma unroll
                         for (int u = 0; u < PH; ++u) {
                             const V3 d = v3(pp[u].x - self.p.x, pp[u].y - self.p.y, pp[u].z - self.p.z);
                             const float m2 = fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x));
-                            keep[u] = k + u < cnt && tt[u] != t_self &&
+                            keep[u] = k + u < cnt && (tt[u] & 0xfffu) != t_self &&
                                       !fov_certainly_culled(self, d, m2, P.cstar);
                         }
 #pragma unroll
                         for (int u = 0; u < PH; ++u)
-                            if (keep[u]) lst[(nb++) * BLOCK] = (uint16_t)tt[u];
+                            if (keep[u]) {  // survivor: keep it and start pulling its velocity in
+                                lst[(nb++) * BLOCK] = (uint16_t)tt[u];
+                                prefetch_l2(vel_s + ((tt[u] & 0xfffu) + S.tslot[tt[u] >> 12]));
+                            }
                     }
-                    // phase 3: exact forces in slot order.  The list ascends, so the row of an
-                    // entry (needed to turn its tile offset back into a slot for the velocity
-                    // gather) only moves forward; the next entry's velocity is prefetched.
-                    int row = 0;
-                    uint32_t row_end = S.toff[1], to_slot = S.ub[0] - S.toff[0];
-                    auto slot_of = [&](uint32_t t) {
-                        while (t >= row_end) {
-                            ++row;
-                            row_end = S.toff[row + 1];
-                            to_slot = S.ub[row] - S.toff[row];
-                        }
-                        return t + to_slot;
-                    };
+                    // phase 3: exact forces in list (= slot) order.  An entry is (row << 12 | tile
+                    // offset); the row turns the offset back into a slot for the velocity gather.
+                    auto slot_of = [&](uint32_t e) { return (e & 0xfffu) + S.tslot[e >> 12]; };
                     // Two entries per trip: their (branch-free) force evaluations are independent
                     // and interleave; the two adds into acc stay in list order.
                     uint32_t t_nx = nb ? lst[0] : 0u;
@@ -269,7 +269,7 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                             t_nx = lst[(k + 2) * BLOCK];
                             v_nx = __ldg(vel_s + slot_of(t_nx));
                         }
-                        const float4 pa = S.tpos[ta], pb = S.tpos[tb];
+                        const float4 pa = S.tpos[ta & 0xfffu], pb = S.tpos[tb & 0xfffu];
                         V3 da, db;
                         const float ma = pair_m2(self, v3(pa.x, pa.y, pa.z), da);
                         const float mb = pair_m2(self, v3(pb.x, pb.y, pb.z), db);
@@ -299,6 +299,7 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                 // ahead of the list stores; full batches carry no tail logic, and the (masked)
                 // tail may read up to PH-1 records past its range -- the tile is padded for that.
                 uint32_t w = (uint32_t)cnt * BLOCK;  // list cursor, in entries
+                const uint32_t tag = (uint32_t)r << 12;
                 auto gate = [&](uint32_t tb, uint32_t live) {
                     float4 pp[PH];
 #pragma unroll
@@ -312,7 +313,7 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
 #pragma unroll
                     for (int u = 0; u < PH; ++u)
                         if ((uint32_t)u < live && !(mm[u] >= P.m2_cut)) {
-                            lst[w] = (uint16_t)(tb + u);
+                            lst[w] = (uint16_t)(tag | (tb + u));
                             w += BLOCK;
                         }
                 };
