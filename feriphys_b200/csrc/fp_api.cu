@@ -931,15 +931,17 @@ int fp_flock_local_len(fp_flock *f, uint64_t *n_local) {
         *n_local = f->n;
         return FP_OK;
     }
-    std::vector<float4> p, v;
-    if ((rc = fetch_owned(f, p, v))) return rc;
-    *n_local = p.size();
-    return FP_OK;
+    return shard_read_local(f->shard, f, n_local, nullptr, nullptr);
 }
 
 int fp_flock_read_local(fp_flock *f, uint64_t *out_index, float *out_aos6) {
     int rc = check(f);
     if (rc) return rc;
+    if (f->shard) {
+        uint64_t n_own = 0;
+        if (!out_index || !out_aos6) { set_error("null output"); return FP_ERR_INVALID; }
+        return shard_read_local(f->shard, f, &n_own, out_index, out_aos6);
+    }
     std::vector<float4> p, v;
     if ((rc = fetch_owned(f, p, v))) return rc;
     if (p.empty()) return FP_OK;

@@ -104,6 +104,7 @@ struct Shard {
     uint32_t *blk_cnt[2] = {nullptr, nullptr};
     size_t blk_cap = 0;
     uint32_t *h_live = nullptr;  // pinned
+    cudaEvent_t ev_live = nullptr;  // completion of the live-count read-back
 };
 
 void shard_index_range(uint64_t n, int rank, int world, uint64_t *first, uint64_t *count) {
@@ -165,6 +166,8 @@ int shard_create(Shard **out, fp_flock *f, int rank, int world, const uint8_t id
         if ((rc = dalloc(&s->all_pos[b], total)) || (rc = dalloc(&s->all_vel[b], total))) return rc;
     if (cudaMallocHost((void **)&s->h_live, 4 * sizeof(uint32_t)) != cudaSuccess)
         return cuda_fail(cudaGetLastError(), "cudaMallocHost", __FILE__, __LINE__);
+    if (cudaEventCreateWithFlags(&s->ev_live, cudaEventDisableTiming) != cudaSuccess)
+        return cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__);
     *out = s;
     return FP_OK;
 }
@@ -179,6 +182,7 @@ void shard_destroy(Shard *s) {
         cudaFree(s->blk_cnt[b]);
     }
     if (s->h_live) cudaFreeHost(s->h_live);
+    if (s->ev_live) cudaEventDestroy(s->ev_live);
     if (s->comm) s->api.CommDestroy(s->comm);
     delete s;
 }
@@ -328,6 +332,42 @@ __global__ void slab_fate_count_kernel(const GridDesc g, int xs0, int xs1, int r
     if (threadIdx.x == 0) {
         blk_l[blockIdx.x] = (uint32_t)cl;
         blk_r[blockIdx.x] = (uint32_t)cr;
+    }
+}
+
+// exclusive scan of two short arrays (per-CTA face counts) in one single-CTA launch
+__global__ void __launch_bounds__(1024) scan2_kernel(uint32_t *a, uint32_t *b, uint32_t n) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s;
+    for (int which = 0; which < 2; ++which) {
+        uint32_t *x = which ? b : a;
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < n; base += 1024) {
+            const uint32_t i = base + threadIdx.x;
+            const uint32_t v = i < n ? x[i] : 0u;
+            uint32_t inc = v;
+            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += t;
+            }
+            if (lane == 31) wsum[w] = inc;
+            __syncthreads();
+            if (w == 0) {
+                uint32_t t = wsum[lane];
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, t, off);
+                    if (lane >= off) t += u;
+                }
+                wsum[lane] = t;
+                if (lane == 31) carry_s = t;
+            }
+            __syncthreads();
+            const uint32_t before = w ? wsum[w - 1] : 0u;
+            if (i < n) x[i] = carry + before + inc - v;
+            carry += carry_s;
+            __syncthreads();
+        }
     }
 }
 
@@ -526,16 +566,6 @@ int shard_grid_fitted(Shard *s, fp_flock *f) {
     s->lgrid = L;
     f->grid = L;
 
-    // one face holds about n / layers boids; 4x head-room plus a floor
-    const uint64_t per_layer = s->n_global / (uint64_t)std::max(G.dim[0], 1) + 1;
-    s->halo_cap = (uint32_t)std::min<uint64_t>(s->n_global, per_layer * 4 + 4096);
-    for (int b = 0; b < 2; ++b) {
-        cudaFree(s->send_pos[b]);
-        cudaFree(s->send_vel[b]);
-        if ((rc = dalloc(&s->send_pos[b], (size_t)s->halo_cap + 1)) ||
-            (rc = dalloc(&s->send_vel[b], (size_t)s->halo_cap + 1)))
-            return rc;
-    }
     // select this rank's slab from the global flock (index order)
     const uint32_t n = (uint32_t)s->n_global;
     const unsigned nb = nblk(n);
@@ -551,7 +581,7 @@ int shard_grid_fitted(Shard *s, fp_flock *f) {
     FP_CUDA(cudaMemcpyAsync(s->h_live, s->blk_cnt[0] + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
     FP_CUDA(cudaStreamSynchronize(f->stream));
     const uint32_t n_own = s->h_live[0];
-    const uint64_t need = (uint64_t)n_own + n_own / 4 + 4ull * (s->halo_cap + 1) + 65536;
+    const uint64_t need = (uint64_t)n_own + n_own / 4 + 65536;  // halo room is added once it is sized
     if ((rc = ensure_local_cap(f, (uint32_t)std::min<uint64_t>(need, 0x7fffffffu)))) { cudaFree(tmp); return rc; }
     slab_select_emit_kernel<<<nb, SB, 0, f->stream>>>(L, s->xs0, s->xs1, s->all_pos[s->acur], s->all_vel[s->acur],
                                                      n, s->blk_cnt[0], f->pos[f->cur], f->vel[f->cur], f->cap,
@@ -563,6 +593,41 @@ int shard_grid_fitted(Shard *s, fp_flock *f) {
     f->n = n_own;
     f->permuted = true;
     s->rep = REP_SLAB;
+
+    // Face messages: size them from the boundary layers as they are now -- the largest face of
+    // any rank (both ends of a message must agree on the size), with 50 % head-room for drift
+    // until the next re-fit.  An overflow raises FP_STATUS_HALO_OVERFLOW.
+    {
+        const unsigned nbo = nblk(std::max(n_own, 1u));
+        if ((rc = ensure_blk(s, nbo))) return rc;
+        FP_CUDA(cudaMemsetAsync(s->blk_cnt[0], 0, ((size_t)nbo + 1) * sizeof(uint32_t), f->stream));
+        FP_CUDA(cudaMemsetAsync(s->blk_cnt[1], 0, ((size_t)nbo + 1) * sizeof(uint32_t), f->stream));
+        slab_fate_count_kernel<<<nbo, SB, 0, f->stream>>>(L, s->xs0, s->xs1, s->rank, s->world, f->pos[f->cur],
+                                                        f->vel[f->cur], n_own, s->blk_cnt[0], s->blk_cnt[1]);
+        scan2_kernel<<<1, 1024, 0, f->stream>>>(s->blk_cnt[0], s->blk_cnt[1], nbo + 1);
+        count_launch(2);
+        // max(left face, right face) on this rank, then max over ranks, on the device
+        uint32_t *d2 = s->blk_cnt[0] + nbo;  // total of array 0; fold array 1's total into it
+        FP_CUDA(cudaMemcpyAsync(s->h_live, s->blk_cnt[0] + nbo, sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
+        FP_CUDA(cudaMemcpyAsync(s->h_live + 1, s->blk_cnt[1] + nbo, sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
+        FP_CUDA(cudaStreamSynchronize(f->stream));
+        s->h_live[2] = std::max(s->h_live[0], s->h_live[1]);
+        FP_CUDA(cudaMemcpyAsync(d2, s->h_live + 2, sizeof(uint32_t), cudaMemcpyHostToDevice, f->stream));
+        FP_NCCL(s, s->api.AllReduce(d2, d2, 1, ncclUint32, ncclMax, s->comm, f->stream));
+        FP_CUDA(cudaMemcpyAsync(s->h_live + 3, d2, sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
+        FP_CUDA(cudaStreamSynchronize(f->stream));
+        const uint64_t face = s->h_live[3];
+        s->halo_cap = (uint32_t)std::min<uint64_t>(s->n_global, face + face / 2 + 4096);
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(s->send_pos[b]);
+            cudaFree(s->send_vel[b]);
+            if ((rc = dalloc(&s->send_pos[b], (size_t)s->halo_cap + 1)) ||
+                (rc = dalloc(&s->send_vel[b], (size_t)s->halo_cap + 1)))
+                return rc;
+        }
+        const uint64_t need2 = (uint64_t)n_own + n_own / 4 + 4ull * (s->halo_cap + 1) + 65536;
+        if ((rc = ensure_local_cap(f, (uint32_t)std::min<uint64_t>(need2, 0x7fffffffu)))) return rc;
+    }
 
     // grid scratch for the largest array a step can sort
     GridWork &w = f->work;
@@ -612,8 +677,8 @@ static int slab_exchange_and_sort(Shard *s, fp_flock *f, uint32_t *n_live) {
     slab_fate_count_kernel<<<nb, SB, 0, f->stream>>>(L, s->xs0, s->xs1, s->rank, s->world, pos, vel, n,
                                                     s->blk_cnt[0], s->blk_cnt[1]);
     count_launch();
-    if ((rc = launch_exclusive_scan(f->stream, s->blk_cnt[0], (size_t)nb + 1, f->work.scan_tmp))) return rc;
-    if ((rc = launch_exclusive_scan(f->stream, s->blk_cnt[1], (size_t)nb + 1, f->work.scan_tmp))) return rc;
+    scan2_kernel<<<1, 1024, 0, f->stream>>>(s->blk_cnt[0], s->blk_cnt[1], nb + 1);
+    count_launch();
     slab_fate_emit_kernel<<<nb, SB, 0, f->stream>>>(L, s->xs0, s->xs1, s->rank, s->world, pos, vel, n,
                                                    s->blk_cnt[0], s->blk_cnt[1], nb, s->send_pos[0],
                                                    s->send_vel[0], s->send_pos[1], s->send_vel[1], hc,
@@ -648,9 +713,12 @@ static int slab_exchange_and_sort(Shard *s, fp_flock *f, uint32_t *n_live) {
     if ((rc = launch_exclusive_scan(f->stream, w.cell_start, (size_t)L.ncells + 2, w.scan_tmp))) return rc;
     FP_CUDA(cudaMemcpyAsync(s->h_live, w.cell_start + L.ncells, sizeof(uint32_t), cudaMemcpyDeviceToHost,
                             f->stream));
+    FP_CUDA(cudaEventRecord(s->ev_live, f->stream));
     int buf = 0;
     if ((rc = launch_radix_sort(f->stream, w, m, L.key_bits, &buf))) return rc;
-    FP_CUDA(cudaStreamSynchronize(f->stream));  // the live count sizes everything downstream
+    // The live count sizes the gather and the walk.  Wait for its copy only: the sort queued
+    // behind it keeps the GPU busy while the host enqueues what follows.
+    FP_CUDA(cudaEventSynchronize(s->ev_live));
     *n_live = s->h_live[0];
     return launch_grid_reorder(f->stream, w.vals[buf], pos, vel, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], *n_live);
 }
@@ -759,6 +827,71 @@ int shard_tap(Shard *s, fp_flock *f, int tap, const TapOut &out) {
         if (rc) return rc;
     }
     return reduce_tap(s, f, tap, out);
+}
+
+// ---- the boids this rank owns, compacted on the device (deterministic order) ----------------
+__global__ void owned_count_kernel(const float4 *__restrict__ vel, uint32_t n, uint32_t *__restrict__ blk) {
+    const uint32_t i = blockIdx.x * SB + threadIdx.x;
+    const bool own = i < n && __float_as_uint(vel[i].w) == REC_OWNED;
+    const int c = __syncthreads_count(own);
+    if (threadIdx.x == 0) blk[blockIdx.x] = (uint32_t)c;
+}
+__global__ void owned_emit_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n,
+                                  const uint32_t *__restrict__ blk_off, unsigned long long *__restrict__ idx,
+                                  float *__restrict__ aos6) {
+    const uint32_t i = blockIdx.x * SB + threadIdx.x;
+    float4 p = make_float4(0, 0, 0, 0), v = p;
+    bool own = false;
+    if (i < n) {
+        p = pos[i];
+        v = vel[i];
+        own = __float_as_uint(v.w) == REC_OWNED;
+    }
+    const uint32_t r = block_rank(own);
+    if (!own) return;
+    const size_t d = blk_off[blockIdx.x] + r;
+    idx[d] = __float_as_uint(p.w);
+    float *o = aos6 + 6 * d;
+    o[0] = p.x; o[1] = p.y; o[2] = p.z;
+    o[3] = v.x; o[4] = v.y; o[5] = v.z;
+}
+
+// count (and, with outputs, fetch) the owned records of the resident array
+int shard_read_local(Shard *s, fp_flock *f, uint64_t *n_local, uint64_t *out_index, float *out_aos6) {
+    const uint32_t n = f->n;
+    *n_local = 0;
+    if (!n) return FP_OK;
+    const unsigned nb = nblk(n);
+    int rc = ensure_blk(s, nb);
+    if (rc) return rc;
+    FP_CUDA(cudaMemsetAsync(s->blk_cnt[0], 0, ((size_t)nb + 1) * sizeof(uint32_t), f->stream));
+    FP_CUDA(cudaMemsetAsync(s->blk_cnt[1], 0, ((size_t)nb + 1) * sizeof(uint32_t), f->stream));
+    owned_count_kernel<<<nb, SB, 0, f->stream>>>(f->vel[f->cur], n, s->blk_cnt[0]);
+    scan2_kernel<<<1, 1024, 0, f->stream>>>(s->blk_cnt[0], s->blk_cnt[1], nb + 1);
+    count_launch(2);
+    FP_CUDA(cudaMemcpyAsync(s->h_live, s->blk_cnt[0] + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    const uint32_t own = s->h_live[0];
+    *n_local = own;
+    if (!out_index || !out_aos6 || !own) return FP_OK;
+    const size_t bytes = (size_t)own * (6 * sizeof(float) + sizeof(unsigned long long));
+    if (bytes > f->stage_bytes) {
+        if (f->d_stage) cudaFree(f->d_stage);
+        f->d_stage = nullptr;
+        f->stage_bytes = 0;
+        FP_CUDA(cudaMalloc(&f->d_stage, bytes));
+        f->stage_bytes = bytes;
+    }
+    unsigned long long *d_idx = (unsigned long long *)f->d_stage;
+    float *d_aos = (float *)(d_idx + own);
+    owned_emit_kernel<<<nb, SB, 0, f->stream>>>(f->pos[f->cur], f->vel[f->cur], n, s->blk_cnt[0], d_idx, d_aos);
+    count_launch();
+    FP_CUDA(cudaGetLastError());
+    FP_CUDA(cudaMemcpyAsync(out_index, d_idx, (size_t)own * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                            f->stream));
+    FP_CUDA(cudaMemcpyAsync(out_aos6, d_aos, (size_t)own * 6 * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    return FP_OK;
 }
 
 int shard_read_state(Shard *s, fp_flock *f, float *out) {

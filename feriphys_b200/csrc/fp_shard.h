@@ -22,6 +22,8 @@ int shard_grid_fitted(Shard *s, fp_flock *f);
 int shard_step(Shard *s, fp_flock *f, uint32_t nsteps);
 int shard_tap(Shard *s, fp_flock *f, int tap, const TapOut &out);
 int shard_read_state(Shard *s, fp_flock *f, float *out_aos6);
+// owned records: count always, contents when the output pointers are non-null
+int shard_read_local(Shard *s, fp_flock *f, uint64_t *n_local, uint64_t *out_index, float *out_aos6);
 // index range [first, first + count) rank owns under the boid-index partition
 void shard_index_range(uint64_t n_global, int rank, int world, uint64_t *first, uint64_t *count);
 
