@@ -423,18 +423,19 @@ def run_ours(args, w, rank, world, local_rank):
     infl_s = infl_ms / 1e3 / steps_seen if w["method_resolved"] != "small" else dev_s / K
     n_local = n / world
     if grid:
-        traffic = None
+        traffic, traffic_src = None, None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch (profiles/)
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
                 t = json.load(fh).get(w["name"])
             if t and t["boids"] == n and world == 1:
-                traffic = {"bytes_per_launch": t["dram_bytes_per_launch"],
-                           "bytes_per_boid": t["dram_bytes_per_launch"] / n, "source": t["source"]}
+                traffic = t["dram_bytes_per_launch"]      # bytes per launch (algorithmic: 64 * n)
+                traffic_src = t["source"]
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": "grid_walk3_kernel<TAP_STEP> (TMA-staged 27-cell walk + extras + Euler)",
                     "achieved": 64.0 * n_local / infl_s / 1e9, "peak": hbm, "unit": "GB/s",
-                    "algorithmic_bytes_per_boid": 64, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_boid": 64, "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": 64 * int(n_local), "peak_source": peak_src,
                     "note": "FP32-issue bound, not HBM bound (ncu: DRAM < 1 % busy, issue slots 66 %); the "
                             "north star names the HBM roofline, so the fraction is reported against it"}
     else:
