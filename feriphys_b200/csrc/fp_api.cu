@@ -236,7 +236,7 @@ int fit_grid(fp_flock *f) {
 
     // scratch
     GridWork &w = f->work;
-    const uint32_t cap = f->shard ? shard_capacity(f->shard) : f->n;
+    const uint32_t cap = f->n;  // (a sharded flock sizes its scratch in shard_grid_fitted)
     const size_t ntiles = ((size_t)cap + 4095) / 4096 + 1;
     const size_t hist = 256 * ntiles;
     const size_t scan_n = std::max(hist, (size_t)g.ncells + 1);
@@ -335,7 +335,7 @@ int run_tap(fp_flock *f, int tap, const TapOut &out) {
         f->cur ^= 1;
         f->permuted = true;
         return launch_grid_walk(f->stream, f->P, f->grid, tap, f->pos[f->cur], f->vel[f->cur],
-                                f->work.cell_start, f->n, nullptr, nullptr, f->d_status, out, nullptr);
+                                f->work.cell_start, f->n, nullptr, nullptr, f->d_status, out);
     }
     int rc = ensure_caller_order(f);
     if (rc) return rc;
@@ -649,7 +649,7 @@ int fp_flock_step(fp_flock *f, uint32_t nsteps) {
             // sorted copy is in pos[cur^1]; the walk overwrites the old buffer
             rc = launch_grid_walk(f->stream, f->P, f->grid, TAP_STEP, f->pos[f->cur ^ 1],
                                   f->vel[f->cur ^ 1], f->work.cell_start, f->n, f->pos[f->cur],
-                                  f->vel[f->cur], f->d_status, TapOut{}, nullptr);
+                                  f->vel[f->cur], f->d_status, TapOut{});
             if (rc) return rc;
             f->permuted = true;
             ++f->steps_since_fit;

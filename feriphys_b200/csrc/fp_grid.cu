@@ -249,7 +249,7 @@ grid_walk2_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
 int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap,
                      const float4 *pos_s, const float4 *vel_s, const uint32_t *cell_start,
                      uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
-                     const TapOut &tap_out, const uint8_t *) {
+                     const TapOut &tap_out) {
     if (!n_all) return FP_OK;
     // FP_WALK_VARIANT (debug/tuning): 1 = one-phase, 2 = three-phase from global memory,
     // 31.. = TMA-staged three-phase tile shapes (fp_walk.cu).  Default: staged.

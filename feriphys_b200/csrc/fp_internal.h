@@ -85,12 +85,12 @@ int launch_radix_sort(cudaStream_t st, GridWork &w, uint32_t n, uint32_t key_bit
 // pos_out[i] = pos_in[vals[i]] (same for vel)
 int launch_grid_reorder(cudaStream_t st, const uint32_t *vals, const float4 *pos_in,
                         const float4 *vel_in, float4 *pos_out, float4 *vel_out, uint32_t n);
-// 27-cell walk over the sorted state.  Rows [row0, row0+nrows) are stepped / tapped;
-// candidates come from all n_all sorted boids (halo included when sharded).
+// 27-cell walk over the n_all sorted records (owned boids are stepped / tapped; ghost
+// and dead records of a sharded flock only serve as candidates).
 int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap,
                      const float4 *pos_s, const float4 *vel_s, const uint32_t *cell_start,
                      uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
-                     const TapOut &tap_out, const uint8_t *owned_mask);
+                     const TapOut &tap_out);
 
 // TMA-staged three-phase walk (fp_walk.cu); variant selects <BLOCK, TILE_CAP, CAP>
 int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, int variant,
@@ -117,7 +117,6 @@ int launch_flock_state_step(cudaStream_t st, float4 *pos, float4 *vel, const flo
                             uint32_t n, uint32_t first_index, float h, int rk4);
 int launch_fastmath_check(uint64_t n, uint64_t seed, uint64_t out_mismatch[2]);
 int launch_bounds(cudaStream_t st, const float4 *pos, uint32_t n, float *out6 /*device*/);
-int launch_fill_u32(cudaStream_t st, uint32_t *p, uint32_t v, size_t n);
 // generic exclusive scan in place over n uint32 (n <= 2^28); tmp >= (n/4096 + 2) elements
 int launch_exclusive_scan(cudaStream_t st, uint32_t *data, size_t n, uint32_t *tmp);
 

@@ -319,22 +319,6 @@ int launch_fastmath_check(uint64_t n, uint64_t seed, uint64_t out_mismatch[2]) {
     return FP_OK;
 }
 
-__global__ void fill_u32_kernel(uint32_t *p, uint32_t v, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-int launch_fill_u32(cudaStream_t st, uint32_t *p, uint32_t v, size_t n) {
-    if (!n) return FP_OK;
-    if (v == 0) {
-        FP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(uint32_t), st));
-        return FP_OK;
-    }
-    fill_u32_kernel<<<blocks_for(n), MB, 0, st>>>(p, v, n);
-    count_launch();
-    FP_CUDA(cudaGetLastError());
-    return FP_OK;
-}
-
 // ---- exclusive scan (uint32, in place): reduce / scan partials / downsweep ----
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;

@@ -187,7 +187,6 @@ void shard_destroy(Shard *s) {
     delete s;
 }
 
-uint32_t shard_capacity(Shard *s) { return s ? (uint32_t)std::min<uint64_t>(s->n_global, 0x7fffffffu) : 0; }
 
 int shard_method(Shard *, int requested, const fp_config &cfg) {
     const float thr = cfg.distance_weight_threshold;
@@ -751,7 +750,7 @@ int shard_step(Shard *s, fp_flock *f, uint32_t nsteps) {
             if ((rc = flock_mark(f))) return rc;
             rc = launch_grid_walk(f->stream, f->P, s->lgrid, TAP_STEP, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1],
                                   f->work.cell_start, n_live, f->pos[f->cur], f->vel[f->cur], f->d_status,
-                                  TapOut{}, nullptr);
+                                  TapOut{});
             if (rc) return rc;
             if ((rc = flock_mark(f))) return rc;
             f->n = n_live;
@@ -818,7 +817,7 @@ int shard_tap(Shard *s, fp_flock *f, int tap, const TapOut &out) {
         f->cur ^= 1;  // the sorted copy (with this step's ghosts) becomes the resident array
         f->n = n_live;
         rc = launch_grid_walk(f->stream, f->P, s->lgrid, tap, f->pos[f->cur], f->vel[f->cur], f->work.cell_start,
-                              n_live, nullptr, nullptr, f->d_status, out, nullptr);
+                              n_live, nullptr, nullptr, f->d_status, out);
         if (rc) return rc;
     } else {
         if ((rc = allpairs_prepare(s, f))) return rc;

@@ -14,7 +14,6 @@ int flock_mark(fp_flock *f);  // timing-hook event
 int shard_unique_id(uint8_t out128[128]);
 int shard_create(Shard **out, fp_flock *f, int rank, int world, const uint8_t id[128]);
 void shard_destroy(Shard *s);
-uint32_t shard_capacity(Shard *s);
 int shard_method(Shard *s, int requested, const fp_config &cfg);
 int shard_reduce_bounds(Shard *s, cudaStream_t st, float lo[3], float hi[3]);
 // called by fit_grid once the GLOBAL grid is known: lay out this rank's slab
