@@ -176,6 +176,7 @@ void free_grid_work(fp_flock *f) {
     dev_free(f->work.cell_start);
     dev_free(f->work.tile_hist);
     dev_free(f->work.scan_tmp);
+    for (auto &p : f->work.soa) dev_free(p);
     f->work = GridWork{};
 }
 
@@ -241,6 +242,15 @@ int fit_grid(fp_flock *f) {
     const size_t hist = 256 * ntiles;
     const size_t scan_n = std::max(hist, (size_t)g.ncells + 1);
     const size_t scan_tmp = scan_n / 4096 + 2;
+    if (cap + 8 > w.soa_cap) {
+        for (auto &p : w.soa) {
+            dev_free(p);
+            int rc = dev_alloc(&p, (size_t)cap + 8);
+            if (rc) return rc;
+            FP_CUDA(cudaMemsetAsync(p, 0, ((size_t)cap + 8) * sizeof(float), f->stream));
+        }
+        w.soa_cap = cap + 8;
+    }
     if (cap > w.cap) {
         dev_free(w.keys[0]); dev_free(w.keys[1]); dev_free(w.vals[0]); dev_free(w.vals[1]);
         int rc;
@@ -310,7 +320,7 @@ int grid_prepare(fp_flock *f) {
     rc = launch_radix_sort(f->stream, f->work, f->n, f->grid.key_bits, &buf);
     if (rc) return rc;
     return launch_grid_reorder(f->stream, f->work.vals[buf], f->pos[f->cur], f->vel[f->cur],
-                               f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], f->n);
+                               f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], f->work.soa, f->n);
 }
 
 void select_leads(fp_flock *f) {
@@ -334,7 +344,7 @@ int run_tap(fp_flock *f, int tap, const TapOut &out) {
         // the sorted copy becomes the state (same boids, new order)
         f->cur ^= 1;
         f->permuted = true;
-        return launch_grid_walk(f->stream, f->P, f->grid, tap, f->pos[f->cur], f->vel[f->cur],
+        return launch_grid_walk(f->stream, f->P, f->grid, tap, f->pos[f->cur], f->vel[f->cur], f->work.soa,
                                 f->work.cell_start, f->n, nullptr, nullptr, f->d_status, out);
     }
     int rc = ensure_caller_order(f);
@@ -648,7 +658,7 @@ int fp_flock_step(fp_flock *f, uint32_t nsteps) {
             if ((rc = mark(f))) return rc;
             // sorted copy is in pos[cur^1]; the walk overwrites the old buffer
             rc = launch_grid_walk(f->stream, f->P, f->grid, TAP_STEP, f->pos[f->cur ^ 1],
-                                  f->vel[f->cur ^ 1], f->work.cell_start, f->n, f->pos[f->cur],
+                                  f->vel[f->cur ^ 1], f->work.soa, f->work.cell_start, f->n, f->pos[f->cur],
                                   f->vel[f->cur], f->d_status, TapOut{});
             if (rc) return rc;
             f->permuted = true;

@@ -50,18 +50,25 @@ int launch_grid_keys(cudaStream_t st, const GridDesc &g, const float4 *pos, uint
 __global__ void __launch_bounds__(GB)
 grid_reorder_kernel(const uint32_t *__restrict__ vals, const float4 *__restrict__ pos_in,
                     const float4 *__restrict__ vel_in, float4 *__restrict__ pos_out,
-                    float4 *__restrict__ vel_out, uint32_t n) {
+                    float4 *__restrict__ vel_out, float *__restrict__ sx, float *__restrict__ sy,
+                    float *__restrict__ sz, uint32_t n) {
     const uint32_t i = blockIdx.x * GB + threadIdx.x;
     if (i >= n) return;
     const uint32_t src = vals[i];
-    pos_out[i] = pos_in[src];
+    const float4 p = pos_in[src];
+    pos_out[i] = p;
     vel_out[i] = vel_in[src];
+    sx[i] = p.x;  // SoA copy of the positions: what the walk stages through TMA
+    sy[i] = p.y;
+    sz[i] = p.z;
 }
 
 int launch_grid_reorder(cudaStream_t st, const uint32_t *vals, const float4 *pos_in,
-                        const float4 *vel_in, float4 *pos_out, float4 *vel_out, uint32_t n) {
+                        const float4 *vel_in, float4 *pos_out, float4 *vel_out, float *const *soa,
+                        uint32_t n) {
     if (!n) return FP_OK;
-    grid_reorder_kernel<<<(n + GB - 1) / GB, GB, 0, st>>>(vals, pos_in, vel_in, pos_out, vel_out, n);
+    grid_reorder_kernel<<<(n + GB - 1) / GB, GB, 0, st>>>(vals, pos_in, vel_in, pos_out, vel_out, soa[0],
+                                                          soa[1], soa[2], n);
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;
@@ -247,9 +254,9 @@ grid_walk2_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
 }
 
 int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap,
-                     const float4 *pos_s, const float4 *vel_s, const uint32_t *cell_start,
-                     uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
-                     const TapOut &tap_out) {
+                     const float4 *pos_s, const float4 *vel_s, const float *const *soa,
+                     const uint32_t *cell_start, uint32_t n_all, float4 *pos_out, float4 *vel_out,
+                     unsigned *status, const TapOut &tap_out) {
     if (!n_all) return FP_OK;
     // FP_WALK_VARIANT (debug/tuning): 1 = one-phase, 2 = three-phase from global memory,
     // 31.. = TMA-staged three-phase tile shapes (fp_walk.cu).  Default: staged.
@@ -260,7 +267,7 @@ int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int
     const dim3 grid((n_all + WALK_BLOCK - 1) / WALK_BLOCK), block(WALK_BLOCK);
     const dim3 grid2((n_all + W2_BLOCK - 1) / W2_BLOCK), block2(W2_BLOCK);
     if ((tap == TAP_STEP || tap == TAP_ACCEL) && variant >= 30)
-        return launch_grid_walk3(st, P, g, tap, variant, pos_s, vel_s, cell_start, n_all, pos_out, vel_out,
+        return launch_grid_walk3(st, P, g, tap, variant, pos_s, vel_s, soa, cell_start, n_all, pos_out, vel_out,
                                  status, tap_out);
     if ((tap == TAP_STEP || tap == TAP_ACCEL) && variant == 1) {
         if (tap == TAP_STEP)

@@ -76,6 +76,8 @@ struct GridWork {  // device scratch owned by the handle
     uint32_t *scan_tmp;    // block partials for the scans
     size_t tile_hist_elems, scan_tmp_elems, cell_cap;
     uint32_t cap;          // boid capacity of keys/vals
+    float *soa[3];         // x, y, z of the sorted state (cap + 8 floats each): the walk's TMA source
+    uint32_t soa_cap;
 };
 
 // keys[0][i] = cell key of pos[i], vals[0][i] = i; cell_start <- exclusive scan of counts
@@ -84,19 +86,20 @@ int launch_grid_keys(cudaStream_t st, const GridDesc &g, const float4 *pos, uint
 int launch_radix_sort(cudaStream_t st, GridWork &w, uint32_t n, uint32_t key_bits, int *out_buf);
 // pos_out[i] = pos_in[vals[i]] (same for vel)
 int launch_grid_reorder(cudaStream_t st, const uint32_t *vals, const float4 *pos_in,
-                        const float4 *vel_in, float4 *pos_out, float4 *vel_out, uint32_t n);
+                        const float4 *vel_in, float4 *pos_out, float4 *vel_out, float *const *soa,
+                        uint32_t n);
 // 27-cell walk over the n_all sorted records (owned boids are stepped / tapped; ghost
 // and dead records of a sharded flock only serve as candidates).
 int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap,
-                     const float4 *pos_s, const float4 *vel_s, const uint32_t *cell_start,
-                     uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
-                     const TapOut &tap_out);
+                     const float4 *pos_s, const float4 *vel_s, const float *const *soa,
+                     const uint32_t *cell_start, uint32_t n_all, float4 *pos_out, float4 *vel_out,
+                     unsigned *status, const TapOut &tap_out);
 
 // TMA-staged three-phase walk (fp_walk.cu); variant selects <BLOCK, TILE_CAP, CAP>
 int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, int variant,
-                      const float4 *pos_s, const float4 *vel_s, const uint32_t *cell_start,
-                      uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
-                      const TapOut &tap_out);
+                      const float4 *pos_s, const float4 *vel_s, const float *const *soa,
+                      const uint32_t *cell_start, uint32_t n_all, float4 *pos_out, float4 *vel_out,
+                      unsigned *status, const TapOut &tap_out);
 
 // ---- misc kernels (fp_misc.cu) ----------------------------------------------
 int launch_aos6_to_soa(cudaStream_t st, const float *aos6, float4 *pos, float4 *vel, uint32_t n,

@@ -644,6 +644,14 @@ int shard_grid_fitted(Shard *s, fp_flock *f) {
         (rc = grow(w.vals[0], w.cap, cap)) || (rc = grow(w.vals[1], w.cap, cap)))
         return rc;
     w.cap = std::max(w.cap, cap);
+    if (cap + 8 > w.soa_cap) {
+        for (auto &p : w.soa) {
+            cudaFree(p);
+            if ((rc = dalloc(&p, (size_t)cap + 8))) return rc;
+            FP_CUDA(cudaMemsetAsync(p, 0, ((size_t)cap + 8) * sizeof(float), f->stream));
+        }
+        w.soa_cap = cap + 8;
+    }
     if ((rc = grow(w.tile_hist, w.tile_hist_elems, hist))) return rc;
     w.tile_hist_elems = std::max(w.tile_hist_elems, hist);
     if ((rc = grow(w.cell_start, w.cell_cap, cells))) return rc;
@@ -719,7 +727,8 @@ static int slab_exchange_and_sort(Shard *s, fp_flock *f, uint32_t *n_live) {
     // behind it keeps the GPU busy while the host enqueues what follows.
     FP_CUDA(cudaEventSynchronize(s->ev_live));
     *n_live = s->h_live[0];
-    return launch_grid_reorder(f->stream, w.vals[buf], pos, vel, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], *n_live);
+    return launch_grid_reorder(f->stream, w.vals[buf], pos, vel, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], w.soa,
+                               *n_live);
 }
 
 static int ensure_slab(Shard *s, fp_flock *f) {
@@ -749,7 +758,7 @@ int shard_step(Shard *s, fp_flock *f, uint32_t nsteps) {
             if ((rc = slab_exchange_and_sort(s, f, &n_live))) return rc;
             if ((rc = flock_mark(f))) return rc;
             rc = launch_grid_walk(f->stream, f->P, s->lgrid, TAP_STEP, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1],
-                                  f->work.cell_start, n_live, f->pos[f->cur], f->vel[f->cur], f->d_status,
+                                  f->work.soa, f->work.cell_start, n_live, f->pos[f->cur], f->vel[f->cur], f->d_status,
                                   TapOut{});
             if (rc) return rc;
             if ((rc = flock_mark(f))) return rc;
@@ -816,7 +825,8 @@ int shard_tap(Shard *s, fp_flock *f, int tap, const TapOut &out) {
         if ((rc = slab_exchange_and_sort(s, f, &n_live))) return rc;
         f->cur ^= 1;  // the sorted copy (with this step's ghosts) becomes the resident array
         f->n = n_live;
-        rc = launch_grid_walk(f->stream, f->P, s->lgrid, tap, f->pos[f->cur], f->vel[f->cur], f->work.cell_start,
+        rc = launch_grid_walk(f->stream, f->P, s->lgrid, tap, f->pos[f->cur], f->vel[f->cur], f->work.soa,
+                              f->work.cell_start,
                               n_live, nullptr, nullptr, f->d_status, out);
         if (rc) return rc;
     } else {

@@ -63,10 +63,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 
 template <int BLOCK, int TILE_CAP, int CAP>
 struct Walk3Smem {
-    float4 tpos[TILE_CAP + 8];   // staged candidate positions (+ padding for masked tail reads)
+    // staged candidate positions, SoA (+ padding for masked tail reads).  SoA so that two
+    // neighbouring candidates load as one 64-bit pair for the packed FP32 gate.
+    alignas(16) float tx[TILE_CAP + 8], ty[TILE_CAP + 8], tz[TILE_CAP + 8];
     uint16_t list[CAP][BLOCK];   // per-thread survivor lists: tile offsets
     uint32_t rng[10][BLOCK];     // per-thread (tile start | len << 16) per row; row 9 = final drain
-    uint32_t ub[9], ue[9];       // CTA-wide slot interval of each row
+    uint32_t ub[9], ue[9];       // CTA-wide slot interval of each row, widened to multiples of 4
     uint32_t toff[10];           // tile offset of each interval (prefix sum)
     uint32_t tslot[9];           // slot - tile offset within each interval (ub[r] - toff[r])
     int fallback;
@@ -90,7 +92,9 @@ __device__ __forceinline__ bool fov_certainly_culled(const Self &s, V3 d, float 
 template <int TAP, int BLOCK, int TILE_CAP, int CAP, int PH>
 __global__ void __launch_bounds__(BLOCK)
 grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__ pos_s,
-                  const float4 *__restrict__ vel_s, const uint32_t *__restrict__ cell_start,
+                  const float4 *__restrict__ vel_s, const float *__restrict__ sx,
+                  const float *__restrict__ sy, const float *__restrict__ sz,
+                  const uint32_t *__restrict__ cell_start,
                   uint32_t n_all, float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
                   unsigned *__restrict__ status, TapOut tap) {
     static_assert(TILE_CAP + 8 <= 4096, "list entries carry a 12-bit tile offset");
@@ -157,18 +161,27 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
         uint32_t total = 0;
         for (int r = 0; r < 9; ++r) {
             S.toff[r] = total;
-            if (S.ue[r] > S.ub[r]) total += S.ue[r] - S.ub[r];
-            else S.ub[r] = S.ue[r] = 0;
+            if (S.ue[r] > S.ub[r]) {  // 16-byte granules for the 4-byte SoA arrays
+                S.ub[r] &= ~3u;
+                S.ue[r] = (S.ue[r] + 3u) & ~3u;
+                total += S.ue[r] - S.ub[r];
+            } else {
+                S.ub[r] = S.ue[r] = 0;
+            }
         }
         S.toff[9] = total;
         for (int r = 0; r < 9; ++r) S.tslot[r] = S.ub[r] - S.toff[r];
         if (total > (uint32_t)TILE_CAP) {
             S.fallback = 1;
         } else if (total > 0) {
-            mbar_expect_tx(&S.bar, total * 16u);
+            mbar_expect_tx(&S.bar, total * 12u);
             for (int r = 0; r < 9; ++r) {
                 const uint32_t len = S.ue[r] - S.ub[r];
-                if (len) bulk_g2s(&S.tpos[S.toff[r]], pos_s + S.ub[r], len * 16u, &S.bar);
+                if (len) {
+                    bulk_g2s(&S.tx[S.toff[r]], sx + S.ub[r], len * 4u, &S.bar);
+                    bulk_g2s(&S.ty[S.toff[r]], sy + S.ub[r], len * 4u, &S.bar);
+                    bulk_g2s(&S.tz[S.toff[r]], sz + S.ub[r], len * 4u, &S.bar);
+                }
             }
         }
     }
@@ -211,6 +224,9 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
         if (S.toff[9] > 0) mbar_wait(&S.bar, 0);
         uint16_t *const lst = &S.list[0][tid];  // entry k at lst[k * BLOCK]
         int cnt = 0;
+        // -p_i broadcast into both halves: p_j + (-p_i) == p_j - p_i exactly
+        const float2 nsx = make_float2(-self.p.x, -self.p.x), nsy = make_float2(-self.p.y, -self.p.y),
+                     nsz = make_float2(-self.p.z, -self.p.z);
 #pragma unroll 1
         for (int r = 0; r <= 9; ++r) {
             const uint32_t pk = S.rng[r][tid];
@@ -228,11 +244,14 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                     int nb = 0;
                     for (int k = 0; k < cnt; k += PH) {
                         uint32_t tt[PH];
-                        float4 pp[PH];
+                        V3 pp[PH];
 #pragma unroll
                         for (int u = 0; u < PH; ++u) tt[u] = lst[min(k + u, cnt - 1) * BLOCK];
 #pragma unroll
-                        for (int u = 0; u < PH; ++u) pp[u] = S.tpos[tt[u] & 0xfffu];
+                        for (int u = 0; u < PH; ++u) {
+                            const uint32_t t = tt[u] & 0xfffu;
+                            pp[u] = v3(S.tx[t], S.ty[t], S.tz[t]);
+                        }
                         bool keep[PH];
 #pragma unroll
                         for (int u = 0; u < PH; ++u) {
@@ -269,7 +288,8 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                             t_nx = lst[(k + 2) * BLOCK];
                             v_nx = __ldg(vel_s + slot_of(t_nx));
                         }
-                        const float4 pa = S.tpos[ta & 0xfffu], pb = S.tpos[tb & 0xfffu];
+                        const uint32_t ia = ta & 0xfffu, ib = tb & 0xfffu;
+                        const V3 pa = v3(S.tx[ia], S.ty[ia], S.tz[ia]), pb = v3(S.tx[ib], S.ty[ib], S.tz[ib]);
                         V3 da, db;
                         const float ma = pair_m2(self, v3(pa.x, pa.y, pa.z), da);
                         const float mb = pair_m2(self, v3(pb.x, pb.y, pb.z), db);
@@ -300,25 +320,41 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
                 // tail may read up to PH-1 records past its range -- the tile is padded for that.
                 uint32_t w = (uint32_t)cnt * BLOCK;  // list cursor, in entries
                 const uint32_t tag = (uint32_t)r << 12;
-                auto gate = [&](uint32_t tb, uint32_t live) {
-                    float4 pp[PH];
+                // Batches of four candidates at an even tile index: two neighbours load as one
+                // 64-bit pair and go through the packed FP32 pipe (FADD2 / FMUL2, sm_100) -- each
+                // half is the same IEEE operation as the scalar form, so m2 is bit-identical.
+                auto gate4 = [&](uint32_t T, uint32_t live) {  // live: bit u set <=> candidate T+u counts
+                    const float2 x01 = *reinterpret_cast<const float2 *>(&S.tx[T]);
+                    const float2 x23 = *reinterpret_cast<const float2 *>(&S.tx[T + 2]);
+                    const float2 y01 = *reinterpret_cast<const float2 *>(&S.ty[T]);
+                    const float2 y23 = *reinterpret_cast<const float2 *>(&S.ty[T + 2]);
+                    const float2 z01 = *reinterpret_cast<const float2 *>(&S.tz[T]);
+                    const float2 z23 = *reinterpret_cast<const float2 *>(&S.tz[T + 2]);
+                    const float2 dx01 = __fadd2_rn(x01, nsx), dx23 = __fadd2_rn(x23, nsx);
+                    const float2 dy01 = __fadd2_rn(y01, nsy), dy23 = __fadd2_rn(y23, nsy);
+                    const float2 dz01 = __fadd2_rn(z01, nsz), dz23 = __fadd2_rn(z23, nsz);
+                    const float2 m01 = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx01, dx01), __fmul2_rn(dy01, dy01)),
+                                                  __fmul2_rn(dz01, dz01));
+                    const float2 m23 = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx23, dx23), __fmul2_rn(dy23, dy23)),
+                                                  __fmul2_rn(dz23, dz23));
+                    const float mm[4] = {m01.x, m01.y, m23.x, m23.y};
 #pragma unroll
-                    for (int u = 0; u < PH; ++u) pp[u] = S.tpos[tb + u];
-                    float mm[PH];
-#pragma unroll
-                    for (int u = 0; u < PH; ++u) {
-                        V3 d;
-                        mm[u] = pair_m2(self, v3(pp[u].x, pp[u].y, pp[u].z), d);
-                    }
-#pragma unroll
-                    for (int u = 0; u < PH; ++u)
-                        if ((uint32_t)u < live && !(mm[u] >= P.m2_cut)) {
-                            lst[w] = (uint16_t)(tag | (tb + u));
+                    for (int u = 0; u < 4; ++u)
+                        if ((live >> u & 1u) && !(mm[u] >= P.m2_cut)) {
+                            lst[w] = (uint16_t)(tag | (T + u));
                             w += BLOCK;
                         }
                 };
-                for (; i + PH <= i1; i += PH) gate(t0 + i, PH);
-                if (i < i1) gate(t0 + i, i1 - i);
+                if (i < i1) {
+                    const uint32_t A = t0 + i, B = t0 + i1;  // tile index range of this pass
+                    uint32_t T = A & ~1u;
+                    if (T < A) {  // odd start: first batch drops the slot before the range
+                        gate4(T, (B - T >= 4 ? 0xeu : ((1u << (B - T)) - 1u) & 0xeu));
+                        T += 4;
+                    }
+                    for (; T + 4 <= B; T += 4) gate4(T, 0xfu);
+                    if (T < B) gate4(T, (1u << (B - T)) - 1u);
+                }
                 i = i1;
                 cnt = (int)(w / BLOCK);
             }
@@ -330,12 +366,14 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
 
 template <int TAP, int BLOCK, int TILE_CAP, int CAP, int PH>
 static int launch3(cudaStream_t st, const DevParams &P, const GridDesc &g, const float4 *pos_s,
-                   const float4 *vel_s, const uint32_t *cell_start, uint32_t n_all, float4 *pos_out,
+                   const float4 *vel_s, const float *const *soa, const uint32_t *cell_start, uint32_t n_all,
+                   float4 *pos_out,
                    float4 *vel_out, unsigned *status, const TapOut &tap_out) {
     auto kern = grid_walk3_kernel<TAP, BLOCK, TILE_CAP, CAP, PH>;
     const int smem = (int)sizeof(Walk3Smem<BLOCK, TILE_CAP, CAP>);
     FP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(n_all + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(P, g, pos_s, vel_s, cell_start, n_all, pos_out,
+    kern<<<(n_all + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(P, g, pos_s, vel_s, soa[0], soa[1], soa[2],
+                                                            cell_start, n_all, pos_out,
                                                             vel_out, status, tap_out);
     count_launch();
     FP_CUDA(cudaGetLastError());
@@ -343,23 +381,24 @@ static int launch3(cudaStream_t st, const DevParams &P, const GridDesc &g, const
 }
 
 int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, int variant,
-                      const float4 *pos_s, const float4 *vel_s, const uint32_t *cell_start,
-                      uint32_t n_all, float4 *pos_out, float4 *vel_out, unsigned *status,
-                      const TapOut &tap_out) {
+                      const float4 *pos_s, const float4 *vel_s, const float *const *soa,
+                      const uint32_t *cell_start, uint32_t n_all, float4 *pos_out, float4 *vel_out,
+                      unsigned *status, const TapOut &tap_out) {
 #define FP_W3(B, T, C, H)                                                                              \
     return tap == TAP_STEP                                                                           \
-               ? launch3<TAP_STEP, B, T, C, H>(st, P, g, pos_s, vel_s, cell_start, n_all, pos_out, vel_out, \
+               ? launch3<TAP_STEP, B, T, C, H>(st, P, g, pos_s, vel_s, soa, cell_start, n_all, pos_out, vel_out, \
                                             status, tap_out)                                         \
-               : launch3<TAP_ACCEL, B, T, C, H>(st, P, g, pos_s, vel_s, cell_start, n_all, pos_out,     \
+               : launch3<TAP_ACCEL, B, T, C, H>(st, P, g, pos_s, vel_s, soa, cell_start, n_all, pos_out,     \
                                              vel_out, status, tap_out)
     switch (variant) {
-        case 31: FP_W3(128, 2048, 64, 4);   // 53 KB: 4 CTAs / SM
-        case 32: FP_W3(128, 2048, 64, 8);
-        case 33: FP_W3(256, 3584, 64, 4);   // 99 KB: 2 CTAs / SM
-        case 34: FP_W3(256, 3584, 64, 8);
-        case 35: FP_W3(64, 1280, 64, 4);    // 31 KB: 7 CTAs / SM
-        case 36: FP_W3(128, 2048, 64, 2);
-        default: FP_W3(128, 2048, 64, 4);
+        case 31: FP_W3(128, 2048, 64, 4);   // 46 KB: 4 CTAs / SM
+        case 32: FP_W3(128, 1792, 64, 4);   // 43 KB: 5 CTAs / SM
+        case 33: FP_W3(128, 1536, 48, 4);   // 36 KB: 6 CTAs / SM
+        case 34: FP_W3(128, 1664, 48, 4);   // 37 KB: 5-6 CTAs / SM
+        case 35: FP_W3(128, 1792, 56, 4);   // 41 KB: 5 CTAs / SM
+        case 36: FP_W3(64, 1024, 64, 4);    // 23 KB: 9 CTAs / SM
+        case 37: FP_W3(64, 1024, 48, 4);    // 21 KB: 10 CTAs / SM
+        default: FP_W3(128, 1792, 64, 4);
     }
 #undef FP_W3
 }
