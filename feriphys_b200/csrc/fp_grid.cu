@@ -262,7 +262,7 @@ int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int
     // 31.. = TMA-staged three-phase tile shapes (fp_walk.cu).  Default: staged.
     static const int variant = [] {
         const char *e = getenv("FP_WALK_VARIANT");
-        return e ? atoi(e) : 31;
+        return e ? atoi(e) : 32;
     }();
     const dim3 grid((n_all + WALK_BLOCK - 1) / WALK_BLOCK), block(WALK_BLOCK);
     const dim3 grid2((n_all + W2_BLOCK - 1) / W2_BLOCK), block2(W2_BLOCK);
