@@ -134,13 +134,17 @@ int ensure_stage(fp_flock *f, size_t bytes) {
     return FP_OK;
 }
 
-int check(fp_flock *f) {
+int settle(fp_flock *f);
+
+// every entry point except fp_flock_step: the handle must be valid and every enqueued step
+// must be known to have happened (lazy re-binning may have voided some: settle replays them)
+int check(fp_flock *f, bool settled = true) {
     if (!f) {
         set_error("null flock handle");
         return FP_ERR_INVALID;
     }
     FP_CUDA(cudaSetDevice(f->device));
-    return FP_OK;
+    return settled ? settle(f) : FP_OK;
 }
 
 int upload_table(fp_flock *f, float **dst, const float *src, size_t floats) {
@@ -176,8 +180,23 @@ void free_grid_work(fp_flock *f) {
     dev_free(f->work.cell_start);
     dev_free(f->work.tile_hist);
     dev_free(f->work.scan_tmp);
-    for (auto &p : f->work.soa) dev_free(p);
+    for (auto &b : f->work.soa) for (auto &p : b) dev_free(p);
+    dev_free(f->work.ctl);
     f->work = GridWork{};
+}
+
+// Planning estimate of the displacement bound one step adds (skin_gate_kernel computes the
+// real one): 25 % margin on the speed, so a plan only fails when the fastest boid gains more.
+float plan_delta(float v2max, float pmax, float dt) {
+    if (!(v2max >= 0.0f)) v2max = INFINITY;
+    return 1.25f * sqrtf(v2max) * fabsf(dt) + pmax * 2.1e-7f + 1e-30f;
+}
+// steps a fresh binning is planned to serve
+int64_t plan_steps(const fp_flock *f, float D, float first_delta) {
+    const float room = f->skin_budget - D - first_delta;
+    if (!(room >= 0.0f)) return 0;
+    const double m = 1.0 + floor((double)room / (double)f->delta_est);
+    return (int64_t)std::min(1.0e6, m * (double)f->plan_scale);
 }
 
 // Fit the uniform grid to the current positions (or the user's domain).
@@ -187,14 +206,11 @@ int fit_grid(fp_flock *f) {
         set_error("grid method needs a finite positive distance_weight_threshold + falloff");
         return FP_ERR_UNSUPPORTED;
     }
-    float lo[3], hi[3];
-    if (f->domain_user) {
-        memcpy(lo, f->user_lo, sizeof(lo));
-        memcpy(hi, f->user_hi, sizeof(hi));
-    } else {
-        int rc = launch_bounds(f->stream, f->pos[f->cur], f->n, f->d_bounds);
+    float lo[3], hi[3], v2max = 0.0f;
+    {
+        int rc = launch_bounds(f->stream, f->pos[f->cur], f->vel[f->cur], f->n, f->d_bounds);
         if (rc) return rc;
-        float b[6];
+        float b[8];
         FP_CUDA(cudaMemcpyAsync(b, f->d_bounds, sizeof(b), cudaMemcpyDeviceToHost, f->stream));
         FP_CUDA(cudaStreamSynchronize(f->stream));
         for (int a = 0; a < 3; ++a) {
@@ -202,11 +218,33 @@ int fit_grid(fp_flock *f) {
             hi[a] = b[3 + a];
             if (!(lo[a] <= hi[a])) lo[a] = hi[a] = 0.0f;
         }
-        if (f->shard) shard_reduce_bounds(f->shard, f->stream, lo, hi);
+        v2max = b[6];
+        if (f->shard) shard_reduce_bounds(f->shard, f->stream, lo, hi, &v2max);
     }
+    float pmax = 0.0f;
+    for (int a = 0; a < 3; ++a) pmax = std::max(pmax, std::max(fabsf(lo[a]), fabsf(hi[a])));
+    if (f->domain_user) {
+        memcpy(lo, f->user_lo, sizeof(lo));
+        memcpy(hi, f->user_hi, sizeof(hi));
+    }
+    // Lazy re-binning: a binning stays exact while every boid is within skin / 2 of where it
+    // was binned, at the price of (1 + skin / reach)^3 more candidates.  The skin that balances
+    // the two for this flock's speed: skin = sqrt(0.29 * delta * reach), delta = the
+    // per-step displacement bound.  Flocks too fast for three steps per binning get none.
+    const float delta = plan_delta(v2max, pmax, f->cfg.dt);
+    float skin = std::min(sqrtf(0.29f * delta * reach), reach / 8.0f);
+    if (!(skin > 0.0f) || !std::isfinite(skin) || skin / 2.0f / delta < 2.0f) skin = 0.0f;
+    {
+        static const char *env = getenv("FP_SKIN");  // tuning: "0" disables, else a fixed skin
+        if (env && *env) skin = std::max(0.0f, (float)atof(env));
+        if (f->skin_override >= 0.0f) skin = f->skin_override;  // fp_flock_set_rebin
+        skin = std::min(skin, 64.0f * reach);
+    }
+    f->skin_budget = skin / 2.0f;
+    f->delta_est = delta;
     // cell edge > reach by a margin that covers the f32 rounding of the cell coordinate
     // (relative 2^-23 of a coordinate < 4096 cells) and of the distance itself.
-    double cell = (double)reach * (1.0 + 1.0 / 512.0);
+    double cell = (double)reach * (1.0 + 1.0 / 512.0) + (double)skin;
     GridDesc g{};
     for (;;) {
         uint64_t ncells = 1;
@@ -232,7 +270,15 @@ int fit_grid(fp_flock *f) {
     g.key_bits = bits;
     g.gdimx = g.dim[0];
     g.xoff = 0;
+    g.skin = skin;
     f->grid = g;
+    f->bin_valid = false;
+    if (!f->work.ctl) {
+        int rc = dev_alloc(&f->work.ctl, 1);
+        if (rc) return rc;
+        FP_CUDA(cudaMemsetAsync(f->work.ctl, 0, sizeof(SkinCtl), f->stream));
+    }
+    if (!f->h_ctl) FP_CUDA(cudaMallocHost((void **)&f->h_ctl, sizeof(SkinCtl)));
     if (f->shard) return shard_grid_fitted(f->shard, f);  // slab layout + scratch are the shard's
 
     // scratch
@@ -243,12 +289,13 @@ int fit_grid(fp_flock *f) {
     const size_t scan_n = std::max(hist, (size_t)g.ncells + 1);
     const size_t scan_tmp = scan_n / 4096 + 2;
     if (cap + 8 > w.soa_cap) {
-        for (auto &p : w.soa) {
-            dev_free(p);
-            int rc = dev_alloc(&p, (size_t)cap + 8);
-            if (rc) return rc;
-            FP_CUDA(cudaMemsetAsync(p, 0, ((size_t)cap + 8) * sizeof(float), f->stream));
-        }
+        for (auto &b : w.soa)
+            for (auto &p : b) {
+                dev_free(p);
+                int rc = dev_alloc(&p, (size_t)cap + 8);
+                if (rc) return rc;
+                FP_CUDA(cudaMemsetAsync(p, 0, ((size_t)cap + 8) * sizeof(float), f->stream));
+            }
         w.soa_cap = cap + 8;
     }
     if (cap > w.cap) {
@@ -305,22 +352,8 @@ int ensure_caller_order(fp_flock *f) {
     if (rc) return rc;
     f->cur ^= 1;
     f->permuted = false;
+    f->bin_valid = false;
     return FP_OK;
-}
-
-// sort the current state by cell; result (sorted) in pos[cur^1], cell_start valid
-int grid_prepare(fp_flock *f) {
-    if (!f->grid_valid || (!f->domain_user && f->steps_since_fit >= 256)) {
-        int rc = fit_grid(f);
-        if (rc) return rc;
-    }
-    int rc = launch_grid_keys(f->stream, f->grid, f->pos[f->cur], f->n, f->work);
-    if (rc) return rc;
-    int buf = 0;
-    rc = launch_radix_sort(f->stream, f->work, f->n, f->grid.key_bits, &buf);
-    if (rc) return rc;
-    return launch_grid_reorder(f->stream, f->work.vals[buf], f->pos[f->cur], f->vel[f->cur],
-                               f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], f->work.soa, f->n);
 }
 
 void select_leads(fp_flock *f) {
@@ -334,18 +367,152 @@ void select_leads(fp_flock *f) {
     }
 }
 
+bool refit_due(const fp_flock *f) {
+    return !f->grid_valid || (!f->domain_user && f->steps_since_fit >= 256);
+}
+
+// Bin the current state: sort it by cell key.  The sorted copy becomes the state (same
+// boids, new order), with its SoA positions, home keys and cell table.  Enqueues only.
+int grid_rebin(fp_flock *f) {
+    GridWork &w = f->work;
+    int rc = launch_skin_gate(f->stream, w.ctl, f->ordinal, 1, f->P.dt, f->skin_budget);
+    if (rc) return rc;
+    if ((rc = launch_grid_keys(f->stream, f->grid, f->pos[f->cur], f->n, w))) return rc;
+    int buf = 0;
+    if ((rc = launch_radix_sort(f->stream, w, f->n, f->grid.key_bits, &buf))) return rc;
+    if ((rc = launch_grid_reorder(f->stream, w.vals[buf], f->pos[f->cur], f->vel[f->cur], f->pos[f->cur ^ 1],
+                                  f->vel[f->cur ^ 1], w.soa[w.soa_cur ^ 1], f->n, w.ctl)))
+        return rc;
+    f->cur ^= 1;
+    w.soa_cur ^= 1;
+    w.home = w.keys[buf];
+    f->permuted = true;
+    f->bin_valid = true;
+    f->plan_left = plan_steps(f, 0.0f, 0.0f);
+    ++f->stat_rebins;
+    return FP_OK;
+}
+
+WalkIO walk_io(fp_flock *f, bool stepping) {
+    GridWork &w = f->work;
+    WalkIO io{};
+    io.pos_s = f->pos[f->cur];
+    io.vel_s = f->vel[f->cur];
+    for (int a = 0; a < 3; ++a) io.soa_in[a] = w.soa[w.soa_cur][a];
+    io.home = w.home;
+    io.cell_start = w.cell_start;
+    io.first = 0;
+    io.last = f->n;
+    if (stepping) {
+        io.pos_out = f->pos[f->cur ^ 1];
+        io.vel_out = f->vel[f->cur ^ 1];
+        for (int a = 0; a < 3; ++a) io.soa_out[a] = w.soa[w.soa_cur ^ 1][a];
+        io.ctl = w.ctl;
+    }
+    return io;
+}
+
+// timing hook: record the next pooled event on the stream (no-op unless timing)
+int mark_event(fp_flock *f) {
+    if (!f->timing) return FP_OK;
+    if (f->ev_used == f->ev_pool.size()) {
+        cudaEvent_t e;
+        FP_CUDA(cudaEventCreate(&e));
+        f->ev_pool.push_back(e);
+    }
+    FP_CUDA(cudaEventRecord(f->ev_pool[f->ev_used++], f->stream));
+    return FP_OK;
+}
+
+// Enqueue `nsteps` grid steps (single GPU).  A step re-bins first when there is no valid
+// binning or the plan says the skin is used up; otherwise it walks the standing binning.
+// Every step is logged as pending until settle() has seen that the device performed it.
+int grid_steps(fp_flock *f, uint32_t nsteps) {
+    int rc;
+    for (uint32_t s = 0; s < nsteps; ++s) {
+        if (f->pending.size() >= 256 && (rc = settle(f))) return rc;
+        if (refit_due(f)) {
+            if ((rc = settle(f)) || (rc = fit_grid(f))) return rc;  // the fit reads the positions
+        }
+        select_leads(f);
+        if ((rc = mark_event(f))) return rc;
+        f->pending.push_back({f->ordinal, f->cur, f->work.soa_cur, f->table_cursor, f->steps_since_fit});
+        if (!f->bin_valid || f->plan_left <= 0) {
+            if ((rc = grid_rebin(f))) return rc;
+        } else if ((rc = launch_skin_gate(f->stream, f->work.ctl, f->ordinal, 0, f->P.dt, f->skin_budget))) {
+            return rc;
+        }
+        if ((rc = mark_event(f))) return rc;
+        if ((rc = launch_grid_walk(f->stream, f->P, f->grid, TAP_STEP, walk_io(f, true), f->d_status, TapOut{})))
+            return rc;
+        f->cur ^= 1;
+        f->work.soa_cur ^= 1;
+        if ((rc = mark_event(f))) return rc;
+        --f->plan_left;
+        ++f->ordinal;
+        ++f->steps_since_fit;
+        ++f->table_cursor;
+        ++f->stat_grid_steps;
+    }
+    return FP_OK;
+}
+
+// Make every enqueued step a fact.  If the device found the skin used up before a step (the
+// flock got faster than planned), that step and all later ones were no-ops: restore the host
+// view to just before it, re-bin and enqueue them again.
+int settle(fp_flock *f) {
+    if (f->shard) return shard_settle(f->shard, f);
+    int rc;
+    while (!f->pending.empty()) {
+        FP_CUDA(cudaMemcpyAsync(f->h_ctl, f->work.ctl, sizeof(SkinCtl), cudaMemcpyDeviceToHost, f->stream));
+        FP_CUDA(cudaStreamSynchronize(f->stream));
+        const SkinCtl c = *f->h_ctl;
+        if (!c.stale) {
+            // refresh the plan from what the device measured
+            float v2, pm;
+            memcpy(&v2, &c.v2max, 4);
+            memcpy(&pm, &c.pmax, 4);
+            f->delta_est = plan_delta(v2, pm, f->cfg.dt);
+            const float last = sqrtf(v2) * fabsf(f->cfg.dt) * 1.000001f + pm * 2.1e-7f + 1e-30f;
+            if (f->bin_valid) f->plan_left = std::min(f->plan_left, plan_steps(f, c.D, last));
+            f->pending.clear();
+            break;
+        }
+        size_t k = 0;
+        while (k < f->pending.size() && f->pending[k].ordinal != c.first_stale) ++k;
+        if (k == f->pending.size()) {
+            set_error("internal: stale step not in the pending log");
+            return FP_ERR_INVALID;
+        }
+        const fp_flock::Pending at = f->pending[k];
+        const uint32_t redo = (uint32_t)(f->pending.size() - k);
+        f->pending.clear();
+        f->cur = at.cur;
+        f->work.soa_cur = at.soa_cur;
+        f->table_cursor = at.table_cursor;
+        f->steps_since_fit = at.steps_since_fit;
+        f->bin_valid = false;
+        f->stat_replayed += redo;
+        f->stat_grid_steps -= redo;
+        FP_CUDA(cudaMemsetAsync(f->work.ctl, 0, sizeof(SkinCtl), f->stream));
+        // the fastest boid outran the plan: let the next fit size the skin for it
+        if (!f->domain_user) f->grid_valid = false;
+        if ((rc = grid_steps(f, redo))) return rc;
+    }
+    return FP_OK;
+}
+
 int run_tap(fp_flock *f, int tap, const TapOut &out) {
     select_leads(f);
     if (f->shard) return shard_tap(f->shard, f, tap, out);
     const int m = resolve_method(f);
     if (m == FP_METHOD_GRID) {
-        int rc = grid_prepare(f);
-        if (rc) return rc;
-        // the sorted copy becomes the state (same boids, new order)
-        f->cur ^= 1;
-        f->permuted = true;
-        return launch_grid_walk(f->stream, f->P, f->grid, tap, f->pos[f->cur], f->vel[f->cur], f->work.soa,
-                                f->work.cell_start, f->n, nullptr, nullptr, f->d_status, out);
+        // (the caller has settled.)  Taps always bin the state where it stands: the listing they
+        // report against is the cell-sorted order of the current positions.
+        int rc;
+        if (refit_due(f) && (rc = fit_grid(f))) return rc;
+        if ((rc = grid_rebin(f))) return rc;
+        return launch_grid_walk(f->stream, f->P, f->grid, tap, walk_io(f, false), f->d_status, out);
     }
     int rc = ensure_caller_order(f);
     if (rc) return rc;
@@ -359,6 +526,8 @@ int run_tap(fp_flock *f, int tap, const TapOut &out) {
 namespace fp {
 int flock_fit_grid(fp_flock *f) { return fit_grid(f); }
 void flock_select_leads(fp_flock *f) { select_leads(f); }
+int64_t flock_plan_steps(const fp_flock *f, float D, float first_delta) { return plan_steps(f, D, first_delta); }
+float flock_plan_delta(float v2max, float pmax, float dt) { return plan_delta(v2max, pmax, dt); }
 }  // namespace fp
 
 // ---- C ABI ----------------------------------------------------------------------
@@ -419,7 +588,7 @@ static int create_common(fp_flock **out, const fp_config *cfg, uint64_t n_global
         if ((rc = dev_alloc(&f->pos[b], f->cap)) || (rc = dev_alloc(&f->vel[b], f->cap))) return fail(rc);
     }
     if ((rc = dev_alloc(&f->d_status, 1)) || (rc = dev_alloc(&f->d_census, 4)) ||
-        (rc = dev_alloc(&f->d_bounds, 6)))
+        (rc = dev_alloc(&f->d_bounds, 8)))
         return fail(rc);
     cudaMemsetAsync(f->d_status, 0, sizeof(unsigned), f->stream);
     refresh_tables(f);
@@ -475,6 +644,7 @@ int fp_flock_destroy(fp_flock *f) {
     dev_free(f->d_status); dev_free(f->d_census); dev_free(f->d_bounds);
     free_grid_work(f);
     if (f->d_stage) cudaFree(f->d_stage);
+    if (f->h_ctl) cudaFreeHost(f->h_ctl);
     for (auto &ev : f->ev_pool) if (ev) cudaEventDestroy(ev);
     if (f->stream) cudaStreamDestroy(f->stream);
     delete f;
@@ -491,6 +661,7 @@ int fp_flock_set_config(fp_flock *f, const fp_config *cfg) {
     f->cfg = *cfg;
     derive_params(f->cfg, f->P);
     if (reach_of(f->cfg) != old_reach) f->grid_valid = false;
+    f->bin_valid = false;  // dt and reach enter the skin accounting
     return FP_OK;
 }
 
@@ -505,6 +676,8 @@ int fp_flock_set_method(fp_flock *f, int method) {
         set_error("bad method");
         return FP_ERR_INVALID;
     }
+    int rc = check(f);
+    if (rc) return rc;
     f->method = method;
     return FP_OK;
 }
@@ -569,14 +742,16 @@ int fp_flock_set_obstacles(fp_flock *f, uint32_t n, const float *o4) {
 }
 
 int fp_flock_set_bbox(fp_flock *f, const float *bbox6) {
-    if (!f) { set_error("null flock handle"); return FP_ERR_INVALID; }
+    int rc = check(f);
+    if (rc) return rc;
     f->P.has_bbox = bbox6 ? 1 : 0;
     if (bbox6) memcpy(f->P.bbox, bbox6, 6 * sizeof(float));
     return FP_OK;
 }
 
 int fp_flock_set_grid_domain(fp_flock *f, const float lo3[3], const float hi3[3]) {
-    if (!f) { set_error("null flock handle"); return FP_ERR_INVALID; }
+    int rc = check(f);
+    if (rc) return rc;
     if (!lo3 || !hi3) {
         f->domain_user = false;
     } else {
@@ -603,30 +778,47 @@ int fp_flock_grid_info(fp_flock *f, uint32_t dims3[3], float *cell_size, uint32_
     return FP_OK;
 }
 
-// timing hook: record the next pooled event on the stream (no-op unless timing)
-static int mark(fp_flock *f) {
-    if (!f->timing) return FP_OK;
-    if (f->ev_used == f->ev_pool.size()) {
-        cudaEvent_t e;
-        FP_CUDA(cudaEventCreate(&e));
-        f->ev_pool.push_back(e);
-    }
-    FP_CUDA(cudaEventRecord(f->ev_pool[f->ev_used++], f->stream));
+int fp_flock_set_rebin(fp_flock *f, float skin, float plan_scale) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (!(plan_scale > 0.0f) || std::isnan(skin)) { set_error("bad re-binning policy"); return FP_ERR_INVALID; }
+    f->skin_override = skin;
+    f->plan_scale = plan_scale;
+    f->grid_valid = false;  // the skin is part of the cell edge
+    f->bin_valid = false;
     return FP_OK;
 }
+
+int fp_flock_rebin_info(fp_flock *f, float *skin, uint64_t *grid_steps, uint64_t *rebins, uint64_t *replayed) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (skin) *skin = f->grid_valid ? f->grid.skin : 0.0f;
+    if (grid_steps) *grid_steps = f->stat_grid_steps;
+    if (rebins) *rebins = f->stat_rebins;
+    if (replayed) *replayed = f->stat_replayed;
+    return FP_OK;
+}
+
+static int mark(fp_flock *f) { return mark_event(f); }
 }  // extern "C"
 namespace fp {
-int flock_mark(fp_flock *f) { return mark(f); }
+int flock_mark(fp_flock *f) { return mark_event(f); }
+int flock_settle_local(fp_flock *f);
 }
 extern "C" {
 
 int fp_flock_step(fp_flock *f, uint32_t nsteps) {
-    int rc = check(f);
+    // grid steps keep running ahead of the host: no settle here (grid_steps / shard_step do it
+    // when they need to); the other methods start from a settled state
+    int rc = check(f, false);
     if (rc) return rc;
     if (nsteps == 0) return FP_OK;
+    if (f->timing) f->timed_steps += nsteps;
     if (f->shard) return shard_step(f->shard, f, nsteps);
     const int m = resolve_method(f);
     if (f->n == 0) return FP_OK;
+    if (m == FP_METHOD_GRID) return grid_steps(f, nsteps);
+    if ((rc = settle(f))) return rc;
     if (m == FP_METHOD_SMALL) {
         rc = ensure_caller_order(f);
         if (rc) return rc;
@@ -652,26 +844,13 @@ int fp_flock_step(fp_flock *f, uint32_t nsteps) {
     for (uint32_t s = 0; s < nsteps; ++s) {
         select_leads(f);
         if ((rc = mark(f))) return rc;
-        if (m == FP_METHOD_GRID) {
-            rc = grid_prepare(f);
-            if (rc) return rc;
-            if ((rc = mark(f))) return rc;
-            // sorted copy is in pos[cur^1]; the walk overwrites the old buffer
-            rc = launch_grid_walk(f->stream, f->P, f->grid, TAP_STEP, f->pos[f->cur ^ 1],
-                                  f->vel[f->cur ^ 1], f->work.soa, f->work.cell_start, f->n, f->pos[f->cur],
-                                  f->vel[f->cur], f->d_status, TapOut{});
-            if (rc) return rc;
-            f->permuted = true;
-            ++f->steps_since_fit;
-        } else {
-            rc = ensure_caller_order(f);
-            if (rc) return rc;
-            if ((rc = mark(f))) return rc;
-            rc = launch_allpairs(f->stream, f->P, TAP_STEP, f->pos[f->cur], f->vel[f->cur], f->n, 0,
-                                 f->n, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], f->d_status, TapOut{});
-            if (rc) return rc;
-            f->cur ^= 1;
-        }
+        rc = ensure_caller_order(f);
+        if (rc) return rc;
+        if ((rc = mark(f))) return rc;
+        rc = launch_allpairs(f->stream, f->P, TAP_STEP, f->pos[f->cur], f->vel[f->cur], f->n, 0,
+                             f->n, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], f->d_status, TapOut{});
+        if (rc) return rc;
+        f->cur ^= 1;
         if ((rc = mark(f))) return rc;
         ++f->table_cursor;
     }
@@ -689,17 +868,19 @@ int fp_flock_timing_begin(fp_flock *f) {
     int rc = check(f);
     if (rc) return rc;
     f->ev_used = 0;
+    f->timed_steps = 0;
     f->timing = true;
     return FP_OK;
 }
 
 int fp_flock_timing_end(fp_flock *f, uint32_t *steps, float *span_ms, float *sort_ms,
                         float *influence_ms) {
-    int rc = check(f);
+    int rc = check(f);  // settles: steps the device voided are replayed inside the timed span
     if (rc) return rc;
+    const size_t k = f->ev_used / 3;  // step triples, replays included
+    if ((rc = mark(f))) return rc;    // closing event
     f->timing = false;
     FP_CUDA(cudaStreamSynchronize(f->stream));
-    const size_t k = f->ev_used / 3;
     float span = 0, so = 0, in = 0;
     for (size_t s = 0; s < k; ++s) {
         float a = 0, b = 0;
@@ -708,9 +889,9 @@ int fp_flock_timing_end(fp_flock *f, uint32_t *steps, float *span_ms, float *sor
         so += a;
         in += b;
     }
-    if (k) FP_CUDA(cudaEventElapsedTime(&span, f->ev_pool[0], f->ev_pool[3 * k - 1]));
+    if (k) FP_CUDA(cudaEventElapsedTime(&span, f->ev_pool[0], f->ev_pool[3 * k]));
     f->ev_used = 0;
-    if (steps) *steps = (uint32_t)k;
+    if (steps) *steps = f->timed_steps;
     if (span_ms) *span_ms = span;
     if (sort_ms) *sort_ms = so;
     if (influence_ms) *influence_ms = in;
@@ -758,6 +939,7 @@ int fp_flock_write_state(fp_flock *f, const float *state) {
         return rc;
     FP_CUDA(cudaStreamSynchronize(f->stream));
     f->permuted = false;
+    f->bin_valid = false;
     if (!f->domain_user) f->grid_valid = false;
     return FP_OK;
 }
@@ -851,6 +1033,7 @@ static int flock_state_step(fp_flock *f, float h, int rk4) {
     TapOut t{};
     t.accel3 = (float *)f->d_stage;
     if ((rc = run_tap(f, TAP_ACCEL, t))) return rc;
+    f->bin_valid = false;  // positions move outside the walk's displacement accounting
     return launch_flock_state_step(f->stream, f->pos[f->cur], f->vel[f->cur], t.accel3, f->n,
                                    f->first_index, h, rk4);
 }

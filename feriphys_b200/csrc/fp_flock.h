@@ -33,6 +33,24 @@ struct fp_flock {
     float user_lo[3]{}, user_hi[3]{};
     uint64_t steps_since_fit = 0;
     fp::GridWork work{};
+    // lazy re-binning (single GPU and sharded): see settle() in fp_api.cu
+    bool bin_valid = false;      // pos[cur] is cell-sorted under `grid`; work.home / cell_start describe it
+    float skin_budget = 0.0f;    // skin / 2: the displacement bound a binning tolerates
+    float delta_est = 0.0f;      // planning estimate of the per-step displacement bound (with margin)
+    int64_t plan_left = 0;       // steps that may still be enqueued before the planned re-binning
+    uint32_t ordinal = 0;        // ordinal of the next step (what the gate kernel records when stale)
+    struct Pending {             // a step that is enqueued but not yet known to have happened
+        uint32_t ordinal;
+        int cur, soa_cur;
+        uint32_t table_cursor;
+        uint64_t steps_since_fit;
+    };
+    std::vector<Pending> pending;
+    fp::SkinCtl *h_ctl = nullptr;  // pinned read-back of work.ctl
+    uint64_t stat_rebins = 0, stat_replayed = 0, stat_grid_steps = 0;
+    uint32_t timed_steps = 0;
+    float skin_override = -1.0f;  // < 0: sized from the flock's speed at every fit
+    float plan_scale = 1.0f;      // stretches the planned steps per binning (tests)
     // staging for host transfers
     void *d_stage = nullptr;
     size_t stage_bytes = 0;

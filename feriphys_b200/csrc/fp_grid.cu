@@ -25,11 +25,7 @@ grid_keys_kernel(const GridDesc g, const float4 *__restrict__ pos, uint32_t n,
     const bool valid = i < n;
     uint32_t key = 0xffffffffu;
     if (valid) {
-        const float4 p = pos[i];
-        const int cx = cell_coord_x(g, p.x);
-        const int cy = cell_coord(p.y, g.origin[1], g.inv_cell, g.dim[1]);
-        const int cz = cell_coord(p.z, g.origin[2], g.inv_cell, g.dim[2]);
-        key = (uint32_t)((cz * g.dim[1] + cy) * g.dim[0] + cx);
+        key = cell_key_of(g, pos[i]);
         keys[i] = key;
     }
     // neighbouring slots usually share a cell: one atomic per distinct key per warp
@@ -51,9 +47,10 @@ __global__ void __launch_bounds__(GB)
 grid_reorder_kernel(const uint32_t *__restrict__ vals, const float4 *__restrict__ pos_in,
                     const float4 *__restrict__ vel_in, float4 *__restrict__ pos_out,
                     float4 *__restrict__ vel_out, float *__restrict__ sx, float *__restrict__ sy,
-                    float *__restrict__ sz, uint32_t n) {
+                    float *__restrict__ sz, uint32_t n, const SkinCtl *__restrict__ ctl) {
     const uint32_t i = blockIdx.x * GB + threadIdx.x;
     if (i >= n) return;
+    if (ctl && ctl->stale) return;  // the steps before this re-binning did not happen: keep the state
     const uint32_t src = vals[i];
     const float4 p = pos_in[src];
     pos_out[i] = p;
@@ -65,28 +62,32 @@ grid_reorder_kernel(const uint32_t *__restrict__ vals, const float4 *__restrict_
 
 int launch_grid_reorder(cudaStream_t st, const uint32_t *vals, const float4 *pos_in,
                         const float4 *vel_in, float4 *pos_out, float4 *vel_out, float *const *soa,
-                        uint32_t n) {
+                        uint32_t n, const SkinCtl *ctl) {
     if (!n) return FP_OK;
     grid_reorder_kernel<<<(n + GB - 1) / GB, GB, 0, st>>>(vals, pos_in, vel_in, pos_out, vel_out, soa[0],
-                                                          soa[1], soa[2], n);
+                                                          soa[1], soa[2], n, ctl);
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;
 }
 
-// K3: one thread per boid of the sorted state.  For each of the 9 (dy, dz) rows
-// the cells cx-1 .. cx+1 are one contiguous slot range of the sorted arrays.
-// Accumulation order: rows (dz, dy) ascending, then slot ascending -- fixed.
+// K3: one thread per boid of the sorted state.  For each of the 9 (dx, dy) rows
+// the cells cz-1 .. cz+1 are one contiguous slot range of the sorted arrays.
+// Accumulation order: rows (dx, dy) ascending, then slot ascending -- fixed.
+// The home cell comes from the key the slot was binned under, not from the current
+// position (lazy re-binning: the position may have drifted by up to skin / 2).
 constexpr int WALK_BLOCK = 128;
 
 template <int TAP>
 __global__ void __launch_bounds__(WALK_BLOCK)
-grid_walk_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__ pos_s,
-                 const float4 *__restrict__ vel_s, const uint32_t *__restrict__ cell_start,
-                 uint32_t n_all, float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
-                 unsigned *__restrict__ status, TapOut tap) {
-    const uint32_t s = blockIdx.x * WALK_BLOCK + threadIdx.x;
-    const bool active = s < n_all;
+grid_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned *__restrict__ status,
+                 TapOut tap) {
+    if (TAP == TAP_STEP && io.ctl && io.ctl->stale) return;
+    const float4 *__restrict__ pos_s = io.pos_s;
+    const float4 *__restrict__ vel_s = io.vel_s;
+    const uint32_t *__restrict__ cell_start = io.cell_start;
+    const uint32_t s = io.first + blockIdx.x * WALK_BLOCK + threadIdx.x;
+    const bool active = s < io.last;
     unsigned long long c_far = 0, c_cull = 0, c_in = 0;
     V3 acc = v3zero();
     uint32_t n_count = 0;
@@ -96,19 +97,21 @@ grid_walk_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__
     if (active) {
         pi4 = pos_s[s];
         vi4 = vel_s[s];
+    }
+    if (TAP == TAP_STEP && io.ctl) track_motion(io.ctl, active, pi4, vi4);
+    if (active) {
         self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
         const bool ghost = __float_as_uint(vi4.w) != 0u;  // halo copy owned by another rank
         const bool need_pairs = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
         if (need_pairs) {
-            const int cx = cell_coord_x(g, pi4.x);
-            const int cy = cell_coord(pi4.y, g.origin[1], g.inv_cell, g.dim[1]);
-            const int cz = cell_coord(pi4.z, g.origin[2], g.inv_cell, g.dim[2]);
-            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
-            for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dim[2] - 1); ++z) {
+            int cx, cy, cz;
+            home_cell(g, __ldg(io.home + s), cx, cy, cz);
+            const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
+            for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x) {
                 for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
-                    const uint32_t rowbase = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
-                    const uint32_t jb = __ldg(cell_start + rowbase + x0);
-                    const uint32_t je = __ldg(cell_start + rowbase + x1 + 1);
+                    const uint32_t rowbase = row_base(g, x, y);
+                    const uint32_t jb = __ldg(cell_start + rowbase + z0);
+                    const uint32_t je = __ldg(cell_start + rowbase + z1 + 1);
                     for (uint32_t j = jb; j < je; ++j) {
                         const float4 pj = __ldg(pos_s + j);
                         if (TAP == TAP_STEP || TAP == TAP_ACCEL) {
@@ -157,32 +160,30 @@ grid_walk_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__
         return;
     }
     if (!active) return;
-    walk_finish<TAP>(P, s, pi4, vi4, self, acc, n_count, n_hash, pos_out, vel_out, status, tap);
+    walk_finish<TAP>(P, s, pi4, vi4, self, acc, n_count, n_hash, io, status, tap);
 }
 
-// K3 (production form for TAP_STEP / TAP_ACCEL): same thread-per-boid walk, same
-// arithmetic and the same summation order as grid_walk_kernel above, but split into
-// three warp-convergent phases so lanes are not idled by the distance and FOV branches
-// (ncu on the one-phase kernel: 9.7 of 32 threads active per instruction):
+// Three-phase form reading candidates from global memory (kept as a cross-check of the staged
+// production kernel in fp_walk.cu, FP_WALK_VARIANT=2): same arithmetic, same summation order.
 //   1. gate   -- every candidate: m2 against m2_cut; survivors' slots are appended to
-//                a per-thread list in shared memory ([entry][thread]: bank == lane, so
-//                any mix of per-lane entry indices is conflict-free);
+//                a per-thread list in shared memory ([entry][thread]: bank == lane);
 //   2. FOV    -- survivors only: exact cosine against cstar; list compacted in place;
 //   3. forces -- visible neighbours only: pair_inrange, accumulated in list (= slot) order.
-// A full list is drained (phases 2+3) before the next chunk of candidates, warp-uniformly.
 constexpr int W2_BLOCK = 128;
 constexpr int W2_CAP = 64;
 
 template <int TAP>
 __global__ void __launch_bounds__(W2_BLOCK)
-grid_walk2_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__ pos_s,
-                  const float4 *__restrict__ vel_s, const uint32_t *__restrict__ cell_start,
-                  uint32_t n_all, float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
-                  unsigned *__restrict__ status, TapOut tap) {
+grid_walk2_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned *__restrict__ status,
+                  TapOut tap) {
+    if (TAP == TAP_STEP && io.ctl && io.ctl->stale) return;
     __shared__ uint32_t list[W2_CAP][W2_BLOCK];
+    const float4 *__restrict__ pos_s = io.pos_s;
+    const float4 *__restrict__ vel_s = io.vel_s;
+    const uint32_t *__restrict__ cell_start = io.cell_start;
     const uint32_t tid = threadIdx.x;
-    const uint32_t s = blockIdx.x * W2_BLOCK + tid;
-    const bool active = s < n_all;
+    const uint32_t s = io.first + blockIdx.x * W2_BLOCK + tid;
+    const bool active = s < io.last;
     float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
     Self self;
     self.p = self.v = self.vhat = v3zero();
@@ -191,12 +192,13 @@ grid_walk2_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
     if (active) {
         pi4 = pos_s[s];
         vi4 = vel_s[s];
+    }
+    if (TAP == TAP_STEP && io.ctl) track_motion(io.ctl, active, pi4, vi4);
+    if (active) {
         self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
         const bool ghost = __float_as_uint(vi4.w) != 0u;
         work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
-        cx = cell_coord_x(g, pi4.x);
-        cy = cell_coord(pi4.y, g.origin[1], g.inv_cell, g.dim[1]);
-        cz = cell_coord(pi4.z, g.origin[2], g.inv_cell, g.dim[2]);
+        home_cell(g, __ldg(io.home + s), cx, cy, cz);
     }
     V3 acc = v3zero();
     int cnt = 0;
@@ -222,17 +224,17 @@ grid_walk2_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
         cnt = 0;
     };
 
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
 #pragma unroll 1
-    for (int dz = -1; dz <= 1; ++dz) {
+    for (int dx = -1; dx <= 1; ++dx) {
 #pragma unroll 1
         for (int dy = -1; dy <= 1; ++dy) {
-            const int z = cz + dz, y = cy + dy;
+            const int x = cx + dx, y = cy + dy;
             uint32_t jb = 0, je = 0;
-            if (work && z >= 0 && z < g.dim[2] && y >= 0 && y < g.dim[1]) {
-                const uint32_t rowbase = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
-                jb = __ldg(cell_start + rowbase + x0);
-                je = __ldg(cell_start + rowbase + x1 + 1);
+            if (work && x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1]) {
+                const uint32_t rowbase = row_base(g, x, y);
+                jb = __ldg(cell_start + rowbase + z0);
+                je = __ldg(cell_start + rowbase + z1 + 1);
             }
             const uint32_t nchunk = __reduce_max_sync(0xffffffffu, (je - jb + W2_CAP - 1) / W2_CAP);
             for (uint32_t c = 0; c < nchunk; ++c) {
@@ -250,53 +252,44 @@ grid_walk2_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
     }
     drain();
     if (!active) return;
-    walk_finish<TAP>(P, s, pi4, vi4, self, acc, 0u, 0ull, pos_out, vel_out, status, tap);
+    walk_finish<TAP>(P, s, pi4, vi4, self, acc, 0u, 0ull, io, status, tap);
 }
 
-int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap,
-                     const float4 *pos_s, const float4 *vel_s, const float *const *soa,
-                     const uint32_t *cell_start, uint32_t n_all, float4 *pos_out, float4 *vel_out,
+int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, const WalkIO &io,
                      unsigned *status, const TapOut &tap_out) {
-    if (!n_all) return FP_OK;
+    if (io.last <= io.first) return FP_OK;
     // FP_WALK_VARIANT (debug/tuning): 1 = one-phase, 2 = three-phase from global memory,
     // 31.. = TMA-staged three-phase tile shapes (fp_walk.cu).  Default: staged.
     static const int variant = [] {
         const char *e = getenv("FP_WALK_VARIANT");
         return e ? atoi(e) : 32;
     }();
-    const dim3 grid((n_all + WALK_BLOCK - 1) / WALK_BLOCK), block(WALK_BLOCK);
-    const dim3 grid2((n_all + W2_BLOCK - 1) / W2_BLOCK), block2(W2_BLOCK);
+    const uint32_t rows = io.last - io.first;
+    const dim3 grid((rows + WALK_BLOCK - 1) / WALK_BLOCK), block(WALK_BLOCK);
+    const dim3 grid2((rows + W2_BLOCK - 1) / W2_BLOCK), block2(W2_BLOCK);
     if ((tap == TAP_STEP || tap == TAP_ACCEL) && variant >= 30)
-        return launch_grid_walk3(st, P, g, tap, variant, pos_s, vel_s, soa, cell_start, n_all, pos_out, vel_out,
-                                 status, tap_out);
+        return launch_grid_walk3(st, P, g, tap, variant, io, status, tap_out);
     if ((tap == TAP_STEP || tap == TAP_ACCEL) && variant == 1) {
         if (tap == TAP_STEP)
-            grid_walk_kernel<TAP_STEP><<<grid, block, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
-                                                               pos_out, vel_out, status, tap_out);
+            grid_walk_kernel<TAP_STEP><<<grid, block, 0, st>>>(P, g, io, status, tap_out);
         else
-            grid_walk_kernel<TAP_ACCEL><<<grid, block, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
-                                                                pos_out, vel_out, status, tap_out);
+            grid_walk_kernel<TAP_ACCEL><<<grid, block, 0, st>>>(P, g, io, status, tap_out);
         count_launch();
         FP_CUDA(cudaGetLastError());
         return FP_OK;
     }
     switch (tap) {
         case TAP_STEP:
-            grid_walk2_kernel<TAP_STEP><<<grid2, block2, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
-                                                                  pos_out, vel_out, status, tap_out);
+            grid_walk2_kernel<TAP_STEP><<<grid2, block2, 0, st>>>(P, g, io, status, tap_out);
             break;
         case TAP_ACCEL:
-            grid_walk2_kernel<TAP_ACCEL><<<grid2, block2, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
-                                                                   pos_out, vel_out, status, tap_out);
+            grid_walk2_kernel<TAP_ACCEL><<<grid2, block2, 0, st>>>(P, g, io, status, tap_out);
             break;
         case TAP_NEIGHBORS:
-            grid_walk_kernel<TAP_NEIGHBORS><<<grid, block, 0, st>>>(P, g, pos_s, vel_s, cell_start,
-                                                                    n_all, pos_out, vel_out, status,
-                                                                    tap_out);
+            grid_walk_kernel<TAP_NEIGHBORS><<<grid, block, 0, st>>>(P, g, io, status, tap_out);
             break;
         default:
-            grid_walk_kernel<TAP_CENSUS><<<grid, block, 0, st>>>(P, g, pos_s, vel_s, cell_start, n_all,
-                                                                 pos_out, vel_out, status, tap_out);
+            grid_walk_kernel<TAP_CENSUS><<<grid, block, 0, st>>>(P, g, io, status, tap_out);
             break;
     }
     count_launch();

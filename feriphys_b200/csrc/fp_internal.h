@@ -52,6 +52,40 @@ struct GridDesc {
     uint32_t key_bits; // bits of ncells (the value ncells itself is the "dead record" key)
     int gdimx;         // global cell layers along x (== dim[0] on a single GPU)
     int xoff;          // global layer index of local layer 0 (0 on a single GPU)
+    float skin;        // cell = reach * (1 + 1/512) + skin: a binning stays exact while every
+                       // boid is within skin / 2 of the position it was binned at
+};
+
+// Device-side control block of the lazy re-binning (fp_misc.cu: skin_gate_kernel).
+struct SkinCtl {
+    float D;               // upper bound on any boid's displacement since the last binning
+    uint32_t v2max;        // bits of max |v|^2 over the inputs of the last walk
+    uint32_t pmax;         // bits of max |coordinate| over the inputs of the last walk
+    uint32_t stale;        // sticky: D exceeded skin / 2 -- every later kernel is a no-op
+    uint32_t first_stale;  // ordinal of the first step that was not performed
+    uint32_t pad[3];
+};
+
+// Sharded grid: a boundary layer of this rank's slab is the neighbour's ghost layer.  The walk
+// writes the advanced state of slots [begin, end) straight into the neighbour's next-step
+// buffers (peer memory over NVLink), record (slot - begin) of its ghost block.  end == 0: off.
+struct PeerFace {
+    uint32_t begin, end;
+    float4 *pos, *vel;
+    float *sx, *sy, *sz;
+};
+
+// Everything one walk launch reads and writes.
+struct WalkIO {
+    const float4 *pos_s, *vel_s;   // cell-sorted records (owned, and ghost copies when sharded)
+    const float *soa_in[3];        // x, y, z of pos_s: the TMA source of the staged walk
+    const uint32_t *home;          // cell key each slot was binned under (owned slots)
+    const uint32_t *cell_start;    // ncells + 1
+    uint32_t first, last;          // slots this launch steps / taps (owned); candidates are any slot
+    float4 *pos_out, *vel_out;     // TAP_STEP: the advanced state, same slots
+    float *soa_out[3];             // TAP_STEP: x, y, z of pos_out
+    SkinCtl *ctl;                  // TAP_STEP: speed tracking + stale check (may be null)
+    PeerFace push[2];              // TAP_STEP, sharded: halo push to the left / right neighbour
 };
 
 // ---- all-pairs (fp_allpairs.cu) --------------------------------------------
@@ -76,8 +110,12 @@ struct GridWork {  // device scratch owned by the handle
     uint32_t *scan_tmp;    // block partials for the scans
     size_t tile_hist_elems, scan_tmp_elems, cell_cap;
     uint32_t cap;          // boid capacity of keys/vals
-    float *soa[3];         // x, y, z of the sorted state (cap + 8 floats each): the walk's TMA source
+    float *soa[2][3];      // x, y, z of the sorted state (cap + 8 floats each), double-buffered like
+                           // pos/vel: the walk's TMA source, rewritten by the walk for the next step
     uint32_t soa_cap;
+    int soa_cur;           // which SoA copy belongs to the current sorted state
+    const uint32_t *home;  // sorted cell keys of the current binning (one of keys[])
+    SkinCtl *ctl;          // device control block
 };
 
 // keys[0][i] = cell key of pos[i], vals[0][i] = i; cell_start <- exclusive scan of counts
@@ -85,21 +123,23 @@ int launch_grid_keys(cudaStream_t st, const GridDesc &g, const float4 *pos, uint
 // stable LSD radix sort of (keys[0], vals[0]) on key bits [0, key_bits); result index in *out_buf
 int launch_radix_sort(cudaStream_t st, GridWork &w, uint32_t n, uint32_t key_bits, int *out_buf);
 // pos_out[i] = pos_in[vals[i]] (same for vel)
+// (no-op when ctl->stale)
 int launch_grid_reorder(cudaStream_t st, const uint32_t *vals, const float4 *pos_in,
                         const float4 *vel_in, float4 *pos_out, float4 *vel_out, float *const *soa,
-                        uint32_t n);
+                        uint32_t n, const SkinCtl *ctl);
 // 27-cell walk over the n_all sorted records (owned boids are stepped / tapped; ghost
 // and dead records of a sharded flock only serve as candidates).
-int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap,
-                     const float4 *pos_s, const float4 *vel_s, const float *const *soa,
-                     const uint32_t *cell_start, uint32_t n_all, float4 *pos_out, float4 *vel_out,
+int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, const WalkIO &io,
                      unsigned *status, const TapOut &tap_out);
 
 // TMA-staged three-phase walk (fp_walk.cu); variant selects <BLOCK, TILE_CAP, CAP>
 int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, int variant,
-                      const float4 *pos_s, const float4 *vel_s, const float *const *soa,
-                      const uint32_t *cell_start, uint32_t n_all, float4 *pos_out, float4 *vel_out,
-                      unsigned *status, const TapOut &tap_out);
+                      const WalkIO &io, unsigned *status, const TapOut &tap_out);
+
+// Lazy re-binning control (fp_misc.cu).  Runs before each grid step: on a re-binning step it
+// resets the displacement bound, otherwise it adds the last walk's bound
+// dt * max|v| + rounding and marks the flock stale when the bound exceeds `budget`.
+int launch_skin_gate(cudaStream_t st, SkinCtl *ctl, uint32_t ordinal, int rebin, float dt, float budget);
 
 // ---- misc kernels (fp_misc.cu) ----------------------------------------------
 int launch_aos6_to_soa(cudaStream_t st, const float *aos6, float4 *pos, float4 *vel, uint32_t n,
@@ -119,7 +159,8 @@ int launch_state_combine_rk4(cudaStream_t st, const float *s, const float *k1, c
 int launch_flock_state_step(cudaStream_t st, float4 *pos, float4 *vel, const float *accel3_by_index,
                             uint32_t n, uint32_t first_index, float h, int rk4);
 int launch_fastmath_check(uint64_t n, uint64_t seed, uint64_t out_mismatch[2]);
-int launch_bounds(cudaStream_t st, const float4 *pos, uint32_t n, float *out6 /*device*/);
+// out8: min xyz, max xyz, max |v|^2, unused
+int launch_bounds(cudaStream_t st, const float4 *pos, const float4 *vel, uint32_t n, float *out8 /*device*/);
 // generic exclusive scan in place over n uint32 (n <= 2^28); tmp >= (n/4096 + 2) elements
 int launch_exclusive_scan(cudaStream_t st, uint32_t *data, size_t n, uint32_t *tmp);
 

@@ -226,7 +226,7 @@ int launch_flock_state_step(cudaStream_t st, float4 *pos, float4 *vel, const flo
     return FP_OK;
 }
 
-// ---- bounds of finite positions: out6 = min xyz, max xyz ---------------------
+// ---- bounds of finite positions: out8 = min xyz, max xyz, max |v|^2, unused ---------------
 __device__ __forceinline__ void atomic_min_f(float *a, float v) {
     // monotone int mapping works for mixed signs with two atomics
     if (v >= 0.0f) atomicMin((int *)a, __float_as_int(v));
@@ -236,8 +236,10 @@ __device__ __forceinline__ void atomic_max_f(float *a, float v) {
     if (v >= 0.0f) atomicMax((int *)a, __float_as_int(v));
     else atomicMin((unsigned *)a, __float_as_uint(v));
 }
-__global__ void bounds_kernel(const float4 *__restrict__ pos, uint32_t n, float *out6) {
+__global__ void bounds_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n,
+                              float *out8) {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float v2 = 0.0f;  // max |v|^2 over finite velocities (sizes the re-binning skin)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pos[i];
         const float c[3] = {p.x, p.y, p.z};
@@ -246,23 +248,59 @@ __global__ void bounds_kernel(const float4 *__restrict__ pos, uint32_t n, float 
                 lo[a] = fminf(lo[a], c[a]);
                 hi[a] = fmaxf(hi[a], c[a]);
             }
+        if (vel) {
+            const float4 v = vel[i];
+            const float m = fmaf(v.z, v.z, fmaf(v.y, v.y, v.x * v.x));
+            if (isfinite(m)) v2 = fmaxf(v2, m);
+        }
     }
+    for (int off = 16; off > 0; off >>= 1) v2 = fmaxf(v2, __shfl_down_sync(0xffffffffu, v2, off));
+    if ((threadIdx.x & 31) == 0 && v2 > 0.0f) atomicMax((unsigned *)(out8 + 6), __float_as_uint(v2));
     for (int a = 0; a < 3; ++a) {
         for (int off = 16; off > 0; off >>= 1) {
             lo[a] = fminf(lo[a], __shfl_down_sync(0xffffffffu, lo[a], off));
             hi[a] = fmaxf(hi[a], __shfl_down_sync(0xffffffffu, hi[a], off));
         }
         if ((threadIdx.x & 31) == 0) {
-            if (lo[a] != INFINITY) atomic_min_f(out6 + a, lo[a]);
-            if (hi[a] != -INFINITY) atomic_max_f(out6 + 3 + a, hi[a]);
+            if (lo[a] != INFINITY) atomic_min_f(out8 + a, lo[a]);
+            if (hi[a] != -INFINITY) atomic_max_f(out8 + 3 + a, hi[a]);
         }
     }
 }
-int launch_bounds(cudaStream_t st, const float4 *pos, uint32_t n, float *out6) {
-    const float init[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    FP_CUDA(cudaMemcpyAsync(out6, init, sizeof(init), cudaMemcpyHostToDevice, st));
+int launch_bounds(cudaStream_t st, const float4 *pos, const float4 *vel, uint32_t n, float *out8) {
+    const float init[8] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0f, 0.0f};
+    FP_CUDA(cudaMemcpyAsync(out8, init, sizeof(init), cudaMemcpyHostToDevice, st));
     if (!n) return FP_OK;
-    bounds_kernel<<<min(blocks_for(n), 148u * 8u), MB, 0, st>>>(pos, n, out6);
+    bounds_kernel<<<min(blocks_for(n), 148u * 8u), MB, 0, st>>>(pos, vel, n, out8);
+    count_launch();
+    FP_CUDA(cudaGetLastError());
+    return FP_OK;
+}
+
+// ---- lazy re-binning control (one thread; see SkinCtl in fp_internal.h) -------------------
+// Displacement bound of one Euler move p' = fl(p + fl(dt * v)): at most dt * |v| (1 + 2^-23)
+// plus half an ulp of the result per component; ulp(p') <= 2^-23 * 2 |p| covers a binade crossing.
+__device__ __host__ inline float skin_step_bound(float v2max, float pmax, float dt) {
+    return sqrtf(v2max) * fabsf(dt) * 1.000001f + pmax * 2.1e-7f + 1e-30f;
+}
+__global__ void skin_gate_kernel(SkinCtl *c, uint32_t ordinal, int rebin, float dt, float budget) {
+    if (c->stale) return;  // sticky until the host settles: nothing after the first void step counts
+    if (rebin) {
+        c->D = 0.0f;  // positions are about to be binned where they are
+    } else {
+        const float D = c->D + skin_step_bound(__uint_as_float(c->v2max), __uint_as_float(c->pmax), dt);
+        c->D = D;
+        if (!(D <= budget)) {  // also catches NaN
+            c->stale = 1u;
+            c->first_stale = ordinal;
+            return;
+        }
+    }
+    c->v2max = 0u;
+    c->pmax = 0u;
+}
+int launch_skin_gate(cudaStream_t st, SkinCtl *ctl, uint32_t ordinal, int rebin, float dt, float budget) {
+    skin_gate_kernel<<<1, 1, 0, st>>>(ctl, ordinal, rebin, dt, budget);
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;

@@ -198,13 +198,13 @@ int shard_method(Shard *, int requested, const fp_config &cfg) {
 }
 
 // lo/hi <- min/max over ranks (device round trip through the flock's bounds scratch is the caller's)
-int shard_reduce_bounds(Shard *s, cudaStream_t st, float lo[3], float hi[3]) {
+int shard_reduce_bounds(Shard *s, cudaStream_t st, float lo[3], float hi[3], float *v2max) {
     float *d = nullptr;
-    FP_CUDA(cudaMalloc((void **)&d, 6 * sizeof(float)));
-    float h[6] = {lo[0], lo[1], lo[2], -hi[0], -hi[1], -hi[2]};  // one ncclMin covers both
+    FP_CUDA(cudaMalloc((void **)&d, 7 * sizeof(float)));
+    float h[7] = {lo[0], lo[1], lo[2], -hi[0], -hi[1], -hi[2], -*v2max};  // one ncclMin covers all
     cudaError_t e = cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st);
     ncclResult_t r = ncclSuccess;
-    if (e == cudaSuccess) r = s->api.AllReduce(d, d, 6, ncclFloat32, ncclMin, s->comm, st);
+    if (e == cudaSuccess) r = s->api.AllReduce(d, d, 7, ncclFloat32, ncclMin, s->comm, st);
     if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d);
@@ -217,6 +217,7 @@ int shard_reduce_bounds(Shard *s, cudaStream_t st, float lo[3], float hi[3]) {
         lo[a] = h[a];
         hi[a] = -h[3 + a];
     }
+    *v2max = -h[6];
     return FP_OK;
 }
 
@@ -434,11 +435,7 @@ __global__ void slab_keys_kernel(const GridDesc g, const float4 *__restrict__ po
             key = g.ncells;
             vel[i] = make_float4(v.x, v.y, v.z, __uint_as_float(REC_DEAD));
         } else {
-            const float4 p = pos[i];
-            const int cx = cell_coord_x(g, p.x);
-            const int cy = cell_coord(p.y, g.origin[1], g.inv_cell, g.dim[1]);
-            const int cz = cell_coord(p.z, g.origin[2], g.inv_cell, g.dim[2]);
-            key = (uint32_t)((cz * g.dim[1] + cy) * g.dim[0] + cx);
+            key = cell_key_of(g, pos[i]);
         }
         keys[i] = key;
     }
@@ -645,11 +642,12 @@ int shard_grid_fitted(Shard *s, fp_flock *f) {
         return rc;
     w.cap = std::max(w.cap, cap);
     if (cap + 8 > w.soa_cap) {
-        for (auto &p : w.soa) {
-            cudaFree(p);
-            if ((rc = dalloc(&p, (size_t)cap + 8))) return rc;
-            FP_CUDA(cudaMemsetAsync(p, 0, ((size_t)cap + 8) * sizeof(float), f->stream));
-        }
+        for (auto &b : w.soa)
+            for (auto &p : b) {
+                cudaFree(p);
+                if ((rc = dalloc(&p, (size_t)cap + 8))) return rc;
+                FP_CUDA(cudaMemsetAsync(p, 0, ((size_t)cap + 8) * sizeof(float), f->stream));
+            }
         w.soa_cap = cap + 8;
     }
     if ((rc = grow(w.tile_hist, w.tile_hist_elems, hist))) return rc;
@@ -727,8 +725,27 @@ static int slab_exchange_and_sort(Shard *s, fp_flock *f, uint32_t *n_live) {
     // behind it keeps the GPU busy while the host enqueues what follows.
     FP_CUDA(cudaEventSynchronize(s->ev_live));
     *n_live = s->h_live[0];
-    return launch_grid_reorder(f->stream, w.vals[buf], pos, vel, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], w.soa,
-                               *n_live);
+    w.home = w.keys[buf];
+    return launch_grid_reorder(f->stream, w.vals[buf], pos, vel, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], w.soa[0],
+                               *n_live, nullptr);
+}
+
+// sorted records in pos/vel[which], SoA copy 0; TAP_STEP output into the other buffer
+static WalkIO slab_walk_io(fp_flock *f, int which, uint32_t n_live, bool stepping) {
+    GridWork &w = f->work;
+    WalkIO io{};
+    io.pos_s = f->pos[which];
+    io.vel_s = f->vel[which];
+    for (int a = 0; a < 3; ++a) io.soa_in[a] = w.soa[0][a];
+    io.home = w.home;
+    io.cell_start = w.cell_start;
+    io.n_all = n_live;
+    if (stepping) {
+        io.pos_out = f->pos[which ^ 1];
+        io.vel_out = f->vel[which ^ 1];
+        for (int a = 0; a < 3; ++a) io.soa_out[a] = w.soa[1][a];
+    }
+    return io;
 }
 
 static int ensure_slab(Shard *s, fp_flock *f) {
@@ -746,6 +763,8 @@ static int allpairs_prepare(Shard *s, fp_flock *f) {
     return to_global(s, f);
 }
 
+int shard_settle(Shard *, fp_flock *) { return FP_OK; }
+
 int shard_step(Shard *s, fp_flock *f, uint32_t nsteps) {
     const int m = shard_method(s, f->method, f->cfg);
     int rc;
@@ -757,9 +776,8 @@ int shard_step(Shard *s, fp_flock *f, uint32_t nsteps) {
             uint32_t n_live = 0;
             if ((rc = slab_exchange_and_sort(s, f, &n_live))) return rc;
             if ((rc = flock_mark(f))) return rc;
-            rc = launch_grid_walk(f->stream, f->P, s->lgrid, TAP_STEP, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1],
-                                  f->work.soa, f->work.cell_start, n_live, f->pos[f->cur], f->vel[f->cur], f->d_status,
-                                  TapOut{});
+            rc = launch_grid_walk(f->stream, f->P, s->lgrid, TAP_STEP, slab_walk_io(f, f->cur ^ 1, n_live, true),
+                                  f->d_status, TapOut{});
             if (rc) return rc;
             if ((rc = flock_mark(f))) return rc;
             f->n = n_live;
@@ -825,9 +843,8 @@ int shard_tap(Shard *s, fp_flock *f, int tap, const TapOut &out) {
         if ((rc = slab_exchange_and_sort(s, f, &n_live))) return rc;
         f->cur ^= 1;  // the sorted copy (with this step's ghosts) becomes the resident array
         f->n = n_live;
-        rc = launch_grid_walk(f->stream, f->P, s->lgrid, tap, f->pos[f->cur], f->vel[f->cur], f->work.soa,
-                              f->work.cell_start,
-                              n_live, nullptr, nullptr, f->d_status, out);
+        rc = launch_grid_walk(f->stream, f->P, s->lgrid, tap, slab_walk_io(f, f->cur, n_live, false), f->d_status,
+                              out);
         if (rc) return rc;
     } else {
         if ((rc = allpairs_prepare(s, f))) return rc;

@@ -9,13 +9,16 @@ namespace fp {
 int flock_fit_grid(fp_flock *f);
 void flock_select_leads(fp_flock *f);
 int flock_mark(fp_flock *f);  // timing-hook event
+int64_t flock_plan_steps(const fp_flock *f, float D, float first_delta);
+float flock_plan_delta(float v2max, float pmax, float dt);
 
 // implemented in fp_shard.cu
 int shard_unique_id(uint8_t out128[128]);
 int shard_create(Shard **out, fp_flock *f, int rank, int world, const uint8_t id[128]);
 void shard_destroy(Shard *s);
 int shard_method(Shard *s, int requested, const fp_config &cfg);
-int shard_reduce_bounds(Shard *s, cudaStream_t st, float lo[3], float hi[3]);
+int shard_reduce_bounds(Shard *s, cudaStream_t st, float lo[3], float hi[3], float *v2max);
+int shard_settle(Shard *s, fp_flock *f);
 // called by fit_grid once the GLOBAL grid is known: lay out this rank's slab
 int shard_grid_fitted(Shard *s, fp_flock *f);
 int shard_step(Shard *s, fp_flock *f, uint32_t nsteps);

@@ -1,7 +1,9 @@
 // fp_walk.cu -- K3, production form: shared-memory staged 27-cell walk.
 //
 // A CTA owns BLOCK consecutive boids of the cell-sorted state (~BLOCK/8 cells
-// of one grid row).  For each of the nine (dy, dz) neighbour rows, everything
+// of one grid row; rows run along z, the fastest key dimension).  A boid's home
+// cell is the key its slot was binned under (lazy re-binning: the position may
+// have drifted by up to skin / 2 since).  For each of the nine (dx, dy) neighbour rows, everything
 // its threads can reach is ONE contiguous slot interval of the sorted position
 // array, so the CTA stages those nine intervals into shared memory with 1-D
 // TMA bulk copies (cp.async.bulk -> UBLKCP) signalled on an mbarrier: every
@@ -91,19 +93,23 @@ __device__ __forceinline__ bool fov_certainly_culled(const Self &s, V3 d, float 
 
 template <int TAP, int BLOCK, int TILE_CAP, int CAP, int PH>
 __global__ void __launch_bounds__(BLOCK)
-grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict__ pos_s,
-                  const float4 *__restrict__ vel_s, const float *__restrict__ sx,
-                  const float *__restrict__ sy, const float *__restrict__ sz,
-                  const uint32_t *__restrict__ cell_start,
-                  uint32_t n_all, float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
-                  unsigned *__restrict__ status, TapOut tap) {
+grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned *__restrict__ status,
+                  TapOut tap) {
     static_assert(TILE_CAP + 8 <= 4096, "list entries carry a 12-bit tile offset");
+    if (TAP == TAP_STEP && io.ctl && io.ctl->stale) return;  // lazy re-binning: this step is void
+    const float4 *__restrict__ pos_s = io.pos_s;
+    const float4 *__restrict__ vel_s = io.vel_s;
+    const float *__restrict__ sx = io.soa_in[0];
+    const float *__restrict__ sy = io.soa_in[1];
+    const float *__restrict__ sz = io.soa_in[2];
+    const uint32_t *__restrict__ cell_start = io.cell_start;
+
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = Walk3Smem<BLOCK, TILE_CAP, CAP>;
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
-    const uint32_t s = blockIdx.x * BLOCK + tid;
-    const bool active = s < n_all;
+    const uint32_t s = io.first + blockIdx.x * BLOCK + tid;
+    const bool active = s < io.last;
 
     if (tid == 0) {
         mbar_init(&S.bar, 1);
@@ -122,25 +128,26 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
     if (active) {
         pi4 = pos_s[s];
         vi4 = vel_s[s];
+    }
+    if (TAP == TAP_STEP && io.ctl) track_motion(io.ctl, active, pi4, vi4);
+    if (active) {
         self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
         const bool ghost = __float_as_uint(vi4.w) != 0u;
         work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
-        cx = cell_coord_x(g, pi4.x);
-        cy = cell_coord(pi4.y, g.origin[1], g.inv_cell, g.dim[1]);
-        cz = cell_coord(pi4.z, g.origin[2], g.inv_cell, g.dim[2]);
+        home_cell(g, __ldg(io.home + s), cx, cy, cz);  // the cell it was binned under
     }
-    // the nine slot ranges of this boid, rows in ascending key order (dz outer, dy inner)
+    // the nine slot ranges of this boid, rows in ascending key order (dx outer, dy inner)
     uint32_t jb[9], je[9];
     {
-        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
 #pragma unroll
         for (int r = 0; r < 9; ++r) {
-            const int z = cz + r / 3 - 1, y = cy + r % 3 - 1;
+            const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
             jb[r] = je[r] = 0;
-            if (work && z >= 0 && z < g.dim[2] && y >= 0 && y < g.dim[1]) {
-                const uint32_t rowbase = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
-                jb[r] = __ldg(cell_start + rowbase + x0);
-                je[r] = __ldg(cell_start + rowbase + x1 + 1);
+            if (work && x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1]) {
+                const uint32_t rowbase = row_base(g, x, y);
+                jb[r] = __ldg(cell_start + rowbase + z0);
+                je[r] = __ldg(cell_start + rowbase + z1 + 1);
             }
         }
     }
@@ -190,12 +197,12 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
     if (S.fallback) {
         // one-phase walk from global memory (dense cluster: the tile would not fit)
         if (work) {
-            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
-            for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dim[2] - 1); ++z) {
+            const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
+            for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x) {
                 for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
-                    const uint32_t rowbase = (uint32_t)((z * g.dim[1] + y) * g.dim[0]);
-                    const uint32_t b = __ldg(cell_start + rowbase + x0);
-                    const uint32_t e = __ldg(cell_start + rowbase + x1 + 1);
+                    const uint32_t rowbase = row_base(g, x, y);
+                    const uint32_t b = __ldg(cell_start + rowbase + z0);
+                    const uint32_t e = __ldg(cell_start + rowbase + z1 + 1);
                     for (uint32_t j = b; j < e; ++j) {
                         if (j == s) continue;
                         const float4 pj = __ldg(pos_s + j);
@@ -361,35 +368,26 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const float4 *__restrict_
         }
     }
     if (!active) return;
-    walk_finish<TAP>(P, s, pi4, vi4, self, acc, 0u, 0ull, pos_out, vel_out, status, tap);
+    walk_finish<TAP>(P, s, pi4, vi4, self, acc, 0u, 0ull, io, status, tap);
 }
 
 template <int TAP, int BLOCK, int TILE_CAP, int CAP, int PH>
-static int launch3(cudaStream_t st, const DevParams &P, const GridDesc &g, const float4 *pos_s,
-                   const float4 *vel_s, const float *const *soa, const uint32_t *cell_start, uint32_t n_all,
-                   float4 *pos_out,
-                   float4 *vel_out, unsigned *status, const TapOut &tap_out) {
+static int launch3(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, unsigned *status,
+                   const TapOut &tap_out) {
     auto kern = grid_walk3_kernel<TAP, BLOCK, TILE_CAP, CAP, PH>;
     const int smem = (int)sizeof(Walk3Smem<BLOCK, TILE_CAP, CAP>);
     FP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(n_all + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(P, g, pos_s, vel_s, soa[0], soa[1], soa[2],
-                                                            cell_start, n_all, pos_out,
-                                                            vel_out, status, tap_out);
+    kern<<<(io.last - io.first + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(P, g, io, status, tap_out);
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;
 }
 
 int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, int variant,
-                      const float4 *pos_s, const float4 *vel_s, const float *const *soa,
-                      const uint32_t *cell_start, uint32_t n_all, float4 *pos_out, float4 *vel_out,
-                      unsigned *status, const TapOut &tap_out) {
-#define FP_W3(B, T, C, H)                                                                              \
-    return tap == TAP_STEP                                                                           \
-               ? launch3<TAP_STEP, B, T, C, H>(st, P, g, pos_s, vel_s, soa, cell_start, n_all, pos_out, vel_out, \
-                                            status, tap_out)                                         \
-               : launch3<TAP_ACCEL, B, T, C, H>(st, P, g, pos_s, vel_s, soa, cell_start, n_all, pos_out,     \
-                                             vel_out, status, tap_out)
+                      const WalkIO &io, unsigned *status, const TapOut &tap_out) {
+#define FP_W3(B, T, C, H)                                                          \
+    return tap == TAP_STEP ? launch3<TAP_STEP, B, T, C, H>(st, P, g, io, status, tap_out) \
+                           : launch3<TAP_ACCEL, B, T, C, H>(st, P, g, io, status, tap_out)
     switch (variant) {
         case 31: FP_W3(128, 2048, 64, 4);   // 46 KB: 4 CTAs / SM
         case 32: FP_W3(128, 1792, 64, 4);   // 43 KB: 5 CTAs / SM

@@ -376,6 +376,16 @@ class Simulation:
         check(self._lib.fp_flock_grid_info(self._h, ptr(dims), C.byref(cell), C.byref(bits)))
         return dims, cell.value, bits.value
 
+    def set_rebin(self, skin: float = -1.0, plan_scale: float = 1.0) -> None:
+        check(self._lib.fp_flock_set_rebin(self._h, skin, plan_scale))
+
+    def rebin_info(self):
+        """-> (skin, grid_steps, rebins, replayed): lazy re-binning of the grid path."""
+        skin = C.c_float(0)
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(self._lib.fp_flock_rebin_info(self._h, C.byref(skin), C.byref(a), C.byref(b), C.byref(c)))
+        return skin.value, a.value, b.value, c.value
+
     def timing_begin(self) -> None:
         check(self._lib.fp_flock_timing_begin(self._h))
 

@@ -133,6 +133,21 @@ int fp_flock_pair_census(fp_flock *f, uint64_t out4[4]);
  * dims[3], cell size and key bits of the grid in use. */
 int fp_flock_set_grid_domain(fp_flock *f, const float lo3[3], const float hi3[3]);
 int fp_flock_grid_info(fp_flock *f, uint32_t dims3[3], float *cell_size, uint32_t *key_bits);
+/* Lazy re-binning of the grid path (ADDITION; the reference has no spatial structure).  The
+ * cell edge carries a skin on top of the interaction reach, so one binning (sort by cell)
+ * serves every step until some boid could have moved skin / 2 from where it was binned --
+ * the device bounds that with max|v| * dt per step and voids a step that would exceed it; the
+ * host re-bins and replays voided steps, so results never depend on the plan.  Neighbour
+ * sets stay exact: the same f32 predicates decide over a superset of candidates.
+ * Reports the skin in use and counters since creation: grid steps performed, binnings,
+ * steps replayed after the device voided them. */
+/* Policy knobs: skin < 0 (default) sizes the skin from the flock's speed at every grid fit,
+ * 0 bins on every step, > 0 fixes it.  plan_scale (default 1) stretches the number of steps
+ * the host plans per binning; values > 1 make the device-side check and the replay do the
+ * work (used by the tests). */
+int fp_flock_set_rebin(fp_flock *f, float skin, float plan_scale);
+int fp_flock_rebin_info(fp_flock *f, float *skin, uint64_t *grid_steps, uint64_t *rebins,
+                        uint64_t *replayed);
 
 /* Device-resident access for callers that already hold device memory
  * (ADDITION).  pos4/vel4 are the SoA float4 arrays of the current state in
