@@ -249,6 +249,14 @@ class Simulation {
         return f;
     }
     void set_method(int m) { fp_check(fp_flock_set_method(h_, m)); }
+    // lazy re-binning of the grid path (ADDITION): skin < 0 = sized from the flock's speed
+    void set_rebin(float skin = -1.0f, float plan_scale = 1.0f) { fp_check(fp_flock_set_rebin(h_, skin, plan_scale)); }
+    struct RebinInfo { float skin; uint64_t grid_steps, rebins, replayed; };
+    RebinInfo rebin_info() {
+        RebinInfo r{};
+        fp_check(fp_flock_rebin_info(h_, &r.skin, &r.grid_steps, &r.rebins, &r.replayed));
+        return r;
+    }
     size_t len() const { return n_; }
     fp_flock *handle() const { return h_; }
     const std::optional<std::vector<LeadBoid>> &lead_boids() const { return lead_boids_; }

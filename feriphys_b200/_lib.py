@@ -68,6 +68,7 @@ _PROTOS = {
     "fp_flock_pair_census": (C.c_int, [_P, _P]),
     "fp_flock_set_grid_domain": (C.c_int, [_P, _P, _P]),
     "fp_flock_grid_info": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "fp_flock_shard_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fp_flock_set_rebin": (C.c_int, [_P, C.c_float, C.c_float]),
     "fp_flock_rebin_info": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_uint64)]),

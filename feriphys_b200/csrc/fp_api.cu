@@ -84,6 +84,8 @@ void derive_params(const fp_config &c, DevParams &P) {
     const float m2_ge_R = smallest_m2([R](float d) { return d >= R; });
     const float m2_gt_thr = smallest_m2([thr](float d) { return !(d <= thr); });
     P.m2_cut = (isnan(m2_ge_R) || isnan(m2_gt_thr)) ? NAN : std::max(m2_ge_R, m2_gt_thr);
+    // the FMA form of dx^2 + dy^2 + dz^2 is within 4e-7 relative of the separately rounded one
+    P.m2_cut_hi = std::isfinite(P.m2_cut) ? nextafterf(P.m2_cut * 1.000001f, INFINITY) + 1e-37f : P.m2_cut;
     // weight 1  <=>  dist <= thr  <=>  m2 <= m2_one
     if (isnan(m2_gt_thr)) P.m2_one = INFINITY;           // every distance is <= thr
     else if (m2_gt_thr == 0.0f) P.m2_one = -1.0f;        // none is
@@ -434,9 +436,12 @@ int grid_steps(fp_flock *f, uint32_t nsteps) {
         if (refit_due(f)) {
             if ((rc = settle(f)) || (rc = fit_grid(f))) return rc;  // the fit reads the positions
         }
+        // a binning never runs inside a window the device may have voided: settle first (one
+        // host sync per binning, i.e. every few dozen steps; it also refreshes the plan)
+        if ((!f->bin_valid || f->plan_left <= 0) && (rc = settle(f))) return rc;
         select_leads(f);
         if ((rc = mark_event(f))) return rc;
-        f->pending.push_back({f->ordinal, f->cur, f->work.soa_cur, f->table_cursor, f->steps_since_fit});
+        f->pending.push_back({f->ordinal, f->cur, f->work.soa_cur, f->table_cursor, f->steps_since_fit, 0u});
         if (!f->bin_valid || f->plan_left <= 0) {
             if ((rc = grid_rebin(f))) return rc;
         } else if ((rc = launch_skin_gate(f->stream, f->work.ctl, f->ordinal, 0, f->P.dt, f->skin_budget))) {
@@ -622,7 +627,9 @@ int fp_flock_create_sharded(fp_flock **out, const fp_config *cfg, uint64_t n_glo
     if (world == 1) return create_common(out, cfg, n_global, 0, n_local, state_aos6, device,
                                          (uint32_t)n_local);
     // slabs are unbalanced by nature: leave head-room for migration and halos
-    const uint64_t cap64 = std::min<uint64_t>(n_global, (n_global / world) * 3 / 2 + (1u << 16));
+    // (at least 2 MB per buffer: cudaIpc exports whole allocations, small ones share blocks)
+    const uint64_t cap64 = std::max<uint64_t>(
+        std::min<uint64_t>(n_global, (n_global / world) * 3 / 2 + (1u << 16)), 1u << 19);
     int rc = create_common(out, cfg, n_global, first_index, n_local, state_aos6, device,
                            (uint32_t)std::max<uint64_t>(cap64, n_local));
     if (rc) return rc;
@@ -1113,6 +1120,16 @@ static int fetch_owned(fp_flock *f, std::vector<float4> &p, std::vector<float4> 
     }
     p.resize(k);
     v.resize(k);
+    return FP_OK;
+}
+
+int fp_flock_shard_info(fp_flock *f, int *rank, int *world, int *peer_mapped) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (rank) *rank = 0;
+    if (world) *world = 1;
+    if (peer_mapped) *peer_mapped = 0;
+    if (f->shard) shard_info(f->shard, rank, world, peer_mapped);
     return FP_OK;
 }
 

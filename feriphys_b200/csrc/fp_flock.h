@@ -38,12 +38,14 @@ struct fp_flock {
     float skin_budget = 0.0f;    // skin / 2: the displacement bound a binning tolerates
     float delta_est = 0.0f;      // planning estimate of the per-step displacement bound (with margin)
     int64_t plan_left = 0;       // steps that may still be enqueued before the planned re-binning
+    uint32_t steps_since_bin = 0;  // sharded: parity of the neighbours' buffers
     uint32_t ordinal = 0;        // ordinal of the next step (what the gate kernel records when stale)
     struct Pending {             // a step that is enqueued but not yet known to have happened
         uint32_t ordinal;
         int cur, soa_cur;
         uint32_t table_cursor;
         uint64_t steps_since_fit;
+        uint32_t steps_since_bin;
     };
     std::vector<Pending> pending;
     fp::SkinCtl *h_ctl = nullptr;  // pinned read-back of work.ctl

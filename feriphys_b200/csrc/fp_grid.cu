@@ -105,7 +105,7 @@ grid_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned 
         const bool need_pairs = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
         if (need_pairs) {
             int cx, cy, cz;
-            home_cell(g, __ldg(io.home + s), cx, cy, cz);
+            home_cell(g, __ldg(io.home + (s - io.first)), cx, cy, cz);
             const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
             for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x) {
                 for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
@@ -198,7 +198,7 @@ grid_walk2_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
         self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
         const bool ghost = __float_as_uint(vi4.w) != 0u;
         work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
-        home_cell(g, __ldg(io.home + s), cx, cy, cz);
+        home_cell(g, __ldg(io.home + (s - io.first)), cx, cy, cz);
     }
     V3 acc = v3zero();
     int cnt = 0;

@@ -63,8 +63,27 @@ struct SkinCtl {
     uint32_t pmax;         // bits of max |coordinate| over the inputs of the last walk
     uint32_t stale;        // sticky: D exceeded skin / 2 -- every later kernel is a no-op
     uint32_t first_stale;  // ordinal of the first step that was not performed
-    uint32_t pad[3];
+    uint32_t g_v2max;      // what the last gate folded into D (sharded: the maximum over all ranks,
+    uint32_t g_pmax;       //  identical on every rank -- the host plans from these)
+    uint32_t fault;        // a peer never posted its step (time-out): the run cannot continue
 };
+
+// Sharded grid: after each walk every rank posts (tag = ordinal + 1, its max |v|^2, max |coord|)
+// into slot [its rank] of EVERY rank's mailbox with peer stores over NVLink.  The next step's
+// gate waits for all tags: that is the step barrier (ghosts pushed by the neighbours' walks have
+// landed) and the all-reduce of the speed bound in one.
+// A rank that has seen all tags may walk and post its NEXT step before a slower rank has read
+// this one, so a mailbox holds two sets of slots, used alternately by tag parity (no rank can
+// be two steps ahead: its next gate needs the slow rank's next post).
+struct Mail {
+    uint32_t tag, v2max, pmax, pad;
+};
+constexpr int FP_MAX_WORLD = 16;
+constexpr int FP_MAIL_SLOTS = 2 * FP_MAX_WORLD;  // [tag & 1][source rank]
+struct MailPeers {
+    Mail *box[FP_MAX_WORLD];  // box[q] = rank q's mailbox (peer-mapped; own entry = local)
+};
+enum { GATE_LOCAL = 0, GATE_REDUCED = 1, GATE_MAILBOX = 2 };
 
 // Sharded grid: a boundary layer of this rank's slab is the neighbour's ghost layer.  The walk
 // writes the advanced state of slots [begin, end) straight into the neighbour's next-step
@@ -139,7 +158,13 @@ int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, in
 // Lazy re-binning control (fp_misc.cu).  Runs before each grid step: on a re-binning step it
 // resets the displacement bound, otherwise it adds the last walk's bound
 // dt * max|v| + rounding and marks the flock stale when the bound exceeds `budget`.
-int launch_skin_gate(cudaStream_t st, SkinCtl *ctl, uint32_t ordinal, int rebin, float dt, float budget);
+// mode GATE_LOCAL: the bound comes from this GPU's walk; GATE_REDUCED: from ctl->g_v2max / g_pmax
+// (an NCCL max-all-reduce put them there); GATE_MAILBOX: wait for `world` tags == ordinal in
+// `mail`, then take the maximum over the posts.
+int launch_skin_gate(cudaStream_t st, SkinCtl *ctl, uint32_t ordinal, int rebin, float dt, float budget,
+                     int mode = GATE_LOCAL, const Mail *mail = nullptr, int world = 1, unsigned *status = nullptr);
+int launch_mail_post(cudaStream_t st, const SkinCtl *ctl, const MailPeers &peers, int world, int rank,
+                     uint32_t tag);
 
 // ---- misc kernels (fp_misc.cu) ----------------------------------------------
 int launch_aos6_to_soa(cudaStream_t st, const float *aos6, float4 *pos, float4 *vel, uint32_t n,

@@ -283,12 +283,54 @@ int launch_bounds(cudaStream_t st, const float4 *pos, const float4 *vel, uint32_
 __device__ __host__ inline float skin_step_bound(float v2max, float pmax, float dt) {
     return sqrtf(v2max) * fabsf(dt) * 1.000001f + pmax * 2.1e-7f + 1e-30f;
 }
-__global__ void skin_gate_kernel(SkinCtl *c, uint32_t ordinal, int rebin, float dt, float budget) {
+__global__ void skin_gate_kernel(SkinCtl *c, uint32_t ordinal, int rebin, float dt, float budget, int mode,
+                                 const Mail *mail, int world, unsigned *status) {
     if (c->stale) return;  // sticky until the host settles: nothing after the first void step counts
+    const int lane = threadIdx.x;  // one warp
+    uint32_t v2 = 0, pm = 0;
+    if (!rebin) {
+        if (mode == GATE_MAILBOX) {
+            bool ok = true;
+            if (lane < world) {
+                const volatile Mail *m = mail + (ordinal & 1u) * FP_MAX_WORLD + lane;
+                const long long t0 = clock64();
+                while (m->tag != ordinal) {
+                    if (clock64() - t0 > 100000000000ll) {  // ~1 min: a peer died or the ranks disagree
+                        ok = false;
+                        break;
+                    }
+                    __nanosleep(64);
+                }
+                __threadfence_system();
+                v2 = m->v2max;
+                pm = m->pmax;
+            }
+            if (!__all_sync(0xffffffffu, ok)) {
+                if (lane == 0) {
+                    c->stale = 1u;
+                    c->first_stale = ordinal;
+                    c->fault = 1u;
+                    if (status) atomicOr(status, 32u);
+                }
+                return;
+            }
+            v2 = __reduce_max_sync(0xffffffffu, v2);
+            pm = __reduce_max_sync(0xffffffffu, pm);
+        } else if (mode == GATE_REDUCED) {
+            v2 = c->g_v2max;
+            pm = c->g_pmax;
+        } else {
+            v2 = c->v2max;
+            pm = c->pmax;
+        }
+    }
+    if (lane != 0) return;
     if (rebin) {
         c->D = 0.0f;  // positions are about to be binned where they are
     } else {
-        const float D = c->D + skin_step_bound(__uint_as_float(c->v2max), __uint_as_float(c->pmax), dt);
+        c->g_v2max = v2;
+        c->g_pmax = pm;
+        const float D = c->D + skin_step_bound(__uint_as_float(v2), __uint_as_float(pm), dt);
         c->D = D;
         if (!(D <= budget)) {  // also catches NaN
             c->stale = 1u;
@@ -299,8 +341,28 @@ __global__ void skin_gate_kernel(SkinCtl *c, uint32_t ordinal, int rebin, float 
     c->v2max = 0u;
     c->pmax = 0u;
 }
-int launch_skin_gate(cudaStream_t st, SkinCtl *ctl, uint32_t ordinal, int rebin, float dt, float budget) {
-    skin_gate_kernel<<<1, 1, 0, st>>>(ctl, ordinal, rebin, dt, budget);
+int launch_skin_gate(cudaStream_t st, SkinCtl *ctl, uint32_t ordinal, int rebin, float dt, float budget, int mode,
+                     const Mail *mail, int world, unsigned *status) {
+    skin_gate_kernel<<<1, 32, 0, st>>>(ctl, ordinal, rebin, dt, budget, mode, mail, world, status);
+    count_launch();
+    FP_CUDA(cudaGetLastError());
+    return FP_OK;
+}
+
+// one thread per destination rank: payload, system fence, then the tag
+__global__ void mail_post_kernel(const SkinCtl *c, MailPeers peers, int world, int rank, uint32_t tag) {
+    if (c->stale) return;
+    const int q = threadIdx.x;
+    if (q >= world) return;
+    Mail *dst = peers.box[q] + (tag & 1u) * FP_MAX_WORLD + rank;
+    dst->v2max = c->v2max;
+    dst->pmax = c->pmax;
+    __threadfence_system();
+    *(volatile uint32_t *)&dst->tag = tag;
+}
+int launch_mail_post(cudaStream_t st, const SkinCtl *ctl, const MailPeers &peers, int world, int rank,
+                     uint32_t tag) {
+    mail_post_kernel<<<1, 32, 0, st>>>(ctl, peers, world, rank, tag);
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;

@@ -10,14 +10,16 @@
 // candidate position is fetched from L2/HBM once per CTA and then re-read ~24
 // times from shared memory.  Each thread then takes its own boid through three
 // warp-convergent phases:
-//   1. gate   -- every candidate: exact squared distance against m2_cut; the
+//   1. gate   -- every candidate: squared distance (packed FP32, fused) against
+//                m2_cut (1 + 1e-6) -- a superset of the in-range pairs; the
 //                survivors' tile offsets (16 bit) go to a per-thread list in
 //                shared memory;
 //   2. FOV    -- survivors only: a cheap approximate cosine drops pairs that are
 //                CERTAINLY culled (margin 1e-5 >> its 1e-6 error bound); anything
 //                near the threshold is kept for the exact test of phase 3;
-//   3. forces -- remaining pairs: the exact pair function (pair_inrange, which
-//                re-tests the FOV exactly), accumulated in list (= slot) order.
+//   3. forces -- remaining pairs: the exact squared distance against m2_cut, then
+//                the exact pair function (pair_inrange, which re-tests the FOV
+//                exactly), accumulated in list (= slot) order.
 // A full list is drained (phases 2+3) before the next chunk, warp-uniformly, and
 // the row loop is kept rolled so the kernel stays inside the instruction cache.
 //
@@ -134,7 +136,7 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
         self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
         const bool ghost = __float_as_uint(vi4.w) != 0u;
         work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
-        home_cell(g, __ldg(io.home + s), cx, cy, cz);  // the cell it was binned under
+        home_cell(g, __ldg(io.home + (s - io.first)), cx, cy, cz);  // the cell it was binned under
     }
     // the nine slot ranges of this boid, rows in ascending key order (dx outer, dy inner)
     uint32_t jb[9], je[9];
@@ -306,13 +308,15 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
                             bool visa, visb;
                             const V3 fa = pair_force_fast(P, self, da, ma, v3(va.x, va.y, va.z), visa);
                             const V3 fb = pair_force_fast(P, self, db, mb, v3(vb.x, vb.y, vb.z), visb);
-                            if (visa) acc = vadd(acc, fa);
-                            if (hasb && visb) acc = vadd(acc, fb);
+                            // (exact distance gate: the pre-gate of phase 1 let a sliver too many through)
+                            if (visa && !(ma >= P.m2_cut)) acc = vadd(acc, fa);
+                            if (hasb && visb && !(mb >= P.m2_cut)) acc = vadd(acc, fb);
                         } else {  // extreme distances (coincident boids, ...): generic exact path
                             V3 contrib;
-                            if (pair_inrange<false>(P, self, da, ma, v3(va.x, va.y, va.z), 1.0f, P.cstar, contrib))
+                            if (!(ma >= P.m2_cut) &&
+                                pair_inrange<false>(P, self, da, ma, v3(va.x, va.y, va.z), 1.0f, P.cstar, contrib))
                                 acc = vadd(acc, contrib);
-                            if (hasb &&
+                            if (hasb && !(mb >= P.m2_cut) &&
                                 pair_inrange<false>(P, self, db, mb, v3(vb.x, vb.y, vb.z), 1.0f, P.cstar, contrib))
                                 acc = vadd(acc, contrib);
                         }
@@ -328,8 +332,10 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
                 uint32_t w = (uint32_t)cnt * BLOCK;  // list cursor, in entries
                 const uint32_t tag = (uint32_t)r << 12;
                 // Batches of four candidates at an even tile index: two neighbours load as one
-                // 64-bit pair and go through the packed FP32 pipe (FADD2 / FMUL2, sm_100) -- each
-                // half is the same IEEE operation as the scalar form, so m2 is bit-identical.
+                // 64-bit pair and go through the packed FP32 pipe (FADD2 / FMUL2 / FFMA2, sm_100).
+                // This is a PRE-gate: the fused sum of squares is within 4e-7 relative of the
+                // reference's separately rounded one, so keeping everything below m2_cut_hi =
+                // m2_cut (1 + 1e-6) keeps a superset; phase 3 re-tests the exact m2 against m2_cut.
                 auto gate4 = [&](uint32_t T, uint32_t live) {  // live: bit u set <=> candidate T+u counts
                     const float2 x01 = *reinterpret_cast<const float2 *>(&S.tx[T]);
                     const float2 x23 = *reinterpret_cast<const float2 *>(&S.tx[T + 2]);
@@ -340,14 +346,12 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
                     const float2 dx01 = __fadd2_rn(x01, nsx), dx23 = __fadd2_rn(x23, nsx);
                     const float2 dy01 = __fadd2_rn(y01, nsy), dy23 = __fadd2_rn(y23, nsy);
                     const float2 dz01 = __fadd2_rn(z01, nsz), dz23 = __fadd2_rn(z23, nsz);
-                    const float2 m01 = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx01, dx01), __fmul2_rn(dy01, dy01)),
-                                                  __fmul2_rn(dz01, dz01));
-                    const float2 m23 = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx23, dx23), __fmul2_rn(dy23, dy23)),
-                                                  __fmul2_rn(dz23, dz23));
+                    const float2 m01 = __ffma2_rn(dz01, dz01, __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01)));
+                    const float2 m23 = __ffma2_rn(dz23, dz23, __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23)));
                     const float mm[4] = {m01.x, m01.y, m23.x, m23.y};
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if ((live >> u & 1u) && !(mm[u] >= P.m2_cut)) {
+                        if ((live >> u & 1u) && !(mm[u] >= P.m2_cut_hi)) {
                             lst[w] = (uint16_t)(tag | (T + u));
                             w += BLOCK;
                         }

@@ -376,6 +376,12 @@ class Simulation:
         check(self._lib.fp_flock_grid_info(self._h, ptr(dims), C.byref(cell), C.byref(bits)))
         return dims, cell.value, bits.value
 
+    def shard_info(self):
+        """-> (rank, world, peer_mapped)"""
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(self._lib.fp_flock_shard_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, bool(c.value)
+
     def set_rebin(self, skin: float = -1.0, plan_scale: float = 1.0) -> None:
         check(self._lib.fp_flock_set_rebin(self._h, skin, plan_scale))
 

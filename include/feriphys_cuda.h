@@ -188,6 +188,10 @@ int fp_nccl_unique_id(uint8_t out128[128]);
 int fp_flock_create_sharded(fp_flock **out, const fp_config *cfg, uint64_t n_global,
                             uint64_t first_index, uint64_t n_local, const float *state_aos6,
                             int device, int rank, int world, const uint8_t nccl_unique_id[128]);
+/* Rank, world size, and whether the grid path's halo exchange runs over peer-mapped memory
+ * (cudaIpc + NVLink stores fused into the walk kernel, mailbox step barrier) or, when the
+ * mapping is unavailable, over ncclSend/ncclRecv.  Unsharded handles report 0, 1, 0. */
+int fp_flock_shard_info(fp_flock *f, int *rank, int *world, int *peer_mapped);
 /* Rows this rank currently owns (grid slabs migrate boids between ranks). */
 int fp_flock_local_len(fp_flock *f, uint64_t *n_local);
 /* Local state with global indices: out_index n_local x u64, out_aos6 n_local x 6. */

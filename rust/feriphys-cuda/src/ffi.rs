@@ -58,6 +58,11 @@ extern "C" {
     pub fn fp_flock_pair_census(f: *mut fp_flock, out4: *mut u64) -> c_int;
     pub fn fp_flock_set_grid_domain(f: *mut fp_flock, lo3: *const f32, hi3: *const f32) -> c_int;
     pub fn fp_flock_grid_info(f: *mut fp_flock, dims3: *mut u32, cell_size: *mut f32, key_bits: *mut u32) -> c_int;
+    pub fn fp_flock_set_rebin(f: *mut fp_flock, skin: f32, plan_scale: f32) -> c_int;
+    pub fn fp_flock_rebin_info(f: *mut fp_flock, skin: *mut f32, grid_steps: *mut u64, rebins: *mut u64,
+                               replayed: *mut u64) -> c_int;
+    pub fn fp_flock_shard_info(f: *mut fp_flock, rank: *mut c_int, world: *mut c_int,
+                               peer_mapped: *mut c_int) -> c_int;
     pub fn fp_flock_device_state(f: *mut fp_flock, pos4: *mut *const c_void, vel4: *mut *const c_void) -> c_int;
     pub fn fp_flock_timing_begin(f: *mut fp_flock) -> c_int;
     pub fn fp_flock_timing_end(f: *mut fp_flock, steps: *mut u32, span_ms: *mut f32, sort_ms: *mut f32,

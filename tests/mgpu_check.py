@@ -47,6 +47,13 @@ def main():
     orc = oracle()
     nt = max(1, (os.cpu_count() or 1) // world)
     c = orc.default_config()
+    if os.environ.get("MGPU_ONLY") == "lazy":
+        lazy_slabs(orc, c, rank, world, local, nt)
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank == 0:
+            print("MGPU_OK", flush=True)
+        return
 
     # ---- all-pairs, all-gather sharded: bit-identical to the oracle -------------------------
     st = synth.uniform_flock(3001, 60.0, seed=81)          # 3001: ragged last rank
@@ -117,10 +124,69 @@ def main():
             cur2, _ = orc.step(c2, sc, cur2, threads=nt, grid=True)
         assert np.abs(got2 - cur2).max() <= 1e-5 * max(1.0, float(np.abs(cur2).max()))
         print(f"[mgpu x{world}] partition switches ok", flush=True)
+    lazy_slabs(orc, c, rank, world, local, nt)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
         print("MGPU_OK", flush=True)
+
+
+def lazy_slabs(orc, c, rank, world, local, nt):
+    """Grid slabs at everyday speeds: one binning serves many steps; in between the walk kernel
+    pushes its boundary boids into the neighbours' ghost blocks over peer memory (or NCCL when
+    FP_SHARD_PEER=0) and the mailbox is the step barrier."""
+    n = 80000
+    st = synth.uniform_flock(n, 380.0, seed=83)
+    sim, sc = make(st, _lib.METHOD_GRID, c, None, local)
+    sim.step_many(7)
+    sim.step_many(53)
+    got = sim.read_state()
+    skin, steps, rebins, replayed = sim.rebin_info()
+    _, _, peer = sim.shard_info()
+    want_peer = os.environ.get("FP_SHARD_PEER", "1") != "0"
+    gc, gh = sim.read_neighbors()
+    idx, loc = sim.read_local()
+    own = torch.tensor([len(idx)], device="cuda")
+    dist.all_reduce(own)
+    assert steps == 60 and replayed == 0 and 2 <= rebins <= 20, (steps, rebins, replayed)
+    assert peer == want_peer, "peer mapping of the halo buffers is not in the expected state"
+    assert np.array_equal(bits(loc), bits(got[idx.astype(np.int64)]))
+    if rank == 0:
+        cur = st
+        for _ in range(60):
+            cur, _ = orc.step(c, sc, cur, threads=nt, grid=True)
+        scale = np.maximum(1.0, np.linalg.norm(cur[:, :3], axis=1))
+        err = (np.linalg.norm(got[:, :3] - cur[:, :3], axis=1) / scale).max()
+        assert err <= 1e-4, err
+        assert int(own[0]) == n
+        rc, rh, _ = orc.neighbors_rows(c, got, threads=nt, grid=True)
+        assert np.array_equal(gc, rc) and np.array_equal(gh, rh), "slab neighbour sets after lazy steps"
+        print(f"[mgpu x{world}] lazy slabs ({'peer stores' if peer else 'nccl messages'}): skin {skin:.3f}, "
+              f"{rebins} binnings / 60 steps, 60-step err {err:.1e}, neighbour sets exact", flush=True)
+    assert sim.status() == 0
+
+    # the plan is 50x too optimistic while an attractor speeds the flock up: every rank must void
+    # the same step on the device and replay it after a fresh (collective) binning
+    tables = dict(attractors=np.array([[-60, 190, 190, 2.0e4]], f32))
+    sim, sc = make(st, _lib.METHOD_GRID, c, tables, local)
+    sim.set_rebin(skin=-1.0, plan_scale=50.0)
+    sim.step_many(80)
+    got = sim.read_state()
+    skin, steps, rebins, replayed = sim.rebin_info()
+    gc, gh = sim.read_neighbors()
+    assert steps == 80 and replayed > 0, (steps, replayed)
+    if rank == 0:
+        cur = st
+        for _ in range(80):
+            cur, _ = orc.step(c, sc, cur, threads=nt, grid=True)
+        scale = np.maximum(1.0, np.linalg.norm(cur[:, :3], axis=1))
+        err = (np.linalg.norm(got[:, :3] - cur[:, :3], axis=1) / scale).max()
+        assert err <= 1e-4, err
+        rc, rh, _ = orc.neighbors_rows(c, got, threads=nt, grid=True)
+        assert np.array_equal(gc, rc) and np.array_equal(gh, rh), "slab neighbour sets after replays"
+        print(f"[mgpu x{world}] outrun plan: {replayed} steps voided on the device and replayed, "
+              f"{rebins} binnings, 80-step err {err:.1e}", flush=True)
+    assert sim.status() == 0
 
 
 if __name__ == "__main__":

@@ -20,3 +20,7 @@ def test_sharded_flock_matches_oracle():
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "mgpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    # the lazy-slab block once more with the halo exchange forced onto NCCL messages
+    env = dict(os.environ, MGPU_ONLY="lazy", FP_SHARD_PEER="0")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
