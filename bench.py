@@ -341,7 +341,7 @@ def run_ours(args, w, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    rb0 = sim.rebin_info() if world == 1 else None
+    rb0 = sim.rebin_info()
     launches0 = lib.fp_launch_count()
     sim.timing_begin()
     t0 = time.perf_counter()
@@ -350,7 +350,7 @@ def run_ours(args, w, rank, world, local_rank):
     wall = time.perf_counter() - t0
     nst, span_ms, sort_ms, infl_ms = sim.timing_end()
     launches = lib.fp_launch_count() - launches0
-    rb1 = sim.rebin_info() if world == 1 else None
+    rb1 = sim.rebin_info()
     clocks = sampler.stop()
     dev_s = span_ms / 1e3
     if dist is not None:
@@ -468,6 +468,9 @@ def run_ours(args, w, rank, world, local_rank):
     if grid and rb0 is not None:
         line["rebinning"] = {"skin": rb1[0], "binnings_in_timed_steps": rb1[2] - rb0[2],
                              "steps_replayed": rb1[3] - rb0[3],
+                             "halo": (("peer stores fused into the walk kernel (cudaIpc over NVLink), mailbox "
+                                       "step barrier" if sim.shard_info()[2] else "ncclSend/ncclRecv after each walk")
+                                      if world > 1 else None),
                              "note": "lazy re-binning: one sort by cell serves every step until some boid "
                                      "could have moved skin/2 (device-checked); the timed steps include "
                                      "their share of binnings"}

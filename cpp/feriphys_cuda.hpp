@@ -57,6 +57,25 @@ struct Duration {
     bool is_zero() const { return secs == 0 && nanos == 0; }
     bool operator<(const Duration &o) const { return secs < o.secs || (secs == o.secs && nanos < o.nanos); }
     bool operator==(const Duration &o) const { return secs == o.secs && nanos == o.nanos; }
+    // impl Add / Sub for Duration: carry in nanoseconds; Sub panics on underflow
+    Duration operator+(const Duration &o) const {
+        Duration r{secs + o.secs, nanos + o.nanos};
+        if (r.nanos >= 1000000000u) {
+            r.nanos -= 1000000000u;
+            ++r.secs;
+        }
+        return r;
+    }
+    Duration operator-(const Duration &o) const {
+        if (*this < o) throw Panic("overflow when subtracting durations");
+        Duration r{secs - o.secs, nanos};
+        if (r.nanos < o.nanos) {
+            --r.secs;
+            r.nanos += 1000000000u;
+        }
+        r.nanos -= o.nanos;
+        return r;
+    }
 };
 
 namespace simulation {

@@ -92,6 +92,11 @@ void derive_params(const fp_config &c, DevParams &P) {
     else P.m2_one = u2f(f2u(m2_gt_thr) - 1);             // predecessor
     P.cstar = acos_threshold(c.max_sight_angle);
     P.cstar_lead = acos_threshold(c.max_sight_angle_to_lead_boid);
+    {
+        const float h = P.cstar - 1e-5f, l = -1.0f + 1e-5f;
+        P.fov_kh = h * fabsf(h);
+        P.fov_kl = l * fabsf(l);
+    }
     P.steer_secs = c.time_to_start_steering_secs;
     P.steer_nanos = c.time_to_start_steering_nanos;
     P.steering_overrides = c.steering_overrides ? 1 : 0;
@@ -248,24 +253,43 @@ int fit_grid(fp_flock *f) {
     // (relative 2^-23 of a coordinate < 4096 cells) and of the distance itself.
     double cell = (double)reach * (1.0 + 1.0 / 512.0) + (double)skin;
     GridDesc g{};
+    static const int zspan_env = [] {
+        const char *e = getenv("FP_GRID_ZSPAN");  // tuning: 1, 2 or 4 (default: as fine as the table allows)
+        return e && *e ? atoi(e) : 0;
+    }();
     for (;;) {
-        uint64_t ncells = 1;
+        uint64_t nxy = 1;
         bool ok = true;
         for (int a = 0; a < 3; ++a) {
             const double ext = (double)hi[a] - (double)lo[a];
             const double d = floor(ext / cell) + 1.0;
             if (!(d <= 4096.0)) { ok = false; break; }
             g.dim[a] = (int)d;
-            ncells *= (uint64_t)g.dim[a];
+            if (a < 2) nxy *= (uint64_t)g.dim[a];
         }
-        if (ok && ncells <= (1ull << 24)) {
-            g.ncells = (uint32_t)ncells;
+        if (ok && nxy * (uint64_t)g.dim[2] <= (1ull << 24)) {
+            // slices along z: as many as keep the cell table within 2^23 entries
+            g.zspan = 1;
+            for (int zs : {4, 2}) {
+                if (zspan_env && zs != zspan_env) continue;
+                const double dz = floor(((double)hi[2] - (double)lo[2]) / (cell / zs)) + 1.0;
+                if (dz <= 16384.0 && (double)nxy * dz <= (double)(1u << 23)) {
+                    g.zspan = zs;
+                    g.dim[2] = (int)dz;
+                    break;
+                }
+            }
+            if (zspan_env == 1) g.zspan = 1;
+            g.ncells = (uint32_t)(nxy * (uint64_t)g.dim[2]);
             break;
         }
         cell *= 1.25;
     }
     g.cell = (float)cell;
     g.inv_cell = 1.0f / g.cell;
+    // z slices: an edge of cell / zspan, still exact -- two boids closer than `cell` along z are
+    // at most zspan slices apart (the 1/512 margin of the edge covers the rounding of zspan / cell)
+    g.inv_cell_z = (float)((double)g.zspan / cell);
     for (int a = 0; a < 3; ++a) g.origin[a] = lo[a];
     uint32_t bits = 1;
     while ((1ull << bits) < g.ncells) ++bits;

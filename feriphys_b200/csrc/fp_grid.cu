@@ -106,7 +106,7 @@ grid_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned 
         if (need_pairs) {
             int cx, cy, cz;
             home_cell(g, __ldg(io.home + (s - io.first)), cx, cy, cz);
-            const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
+            const int z0 = max(cz - g.zspan, 0), z1 = min(cz + g.zspan, g.dim[2] - 1);
             for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x) {
                 for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
                     const uint32_t rowbase = row_base(g, x, y);
@@ -224,7 +224,7 @@ grid_walk2_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
         cnt = 0;
     };
 
-    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
+    const int z0 = max(cz - g.zspan, 0), z1 = min(cz + g.zspan, g.dim[2] - 1);
 #pragma unroll 1
     for (int dx = -1; dx <= 1; ++dx) {
 #pragma unroll 1
@@ -262,7 +262,7 @@ int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int
     // 31.. = TMA-staged three-phase tile shapes (fp_walk.cu).  Default: staged.
     static const int variant = [] {
         const char *e = getenv("FP_WALK_VARIANT");
-        return e ? atoi(e) : 32;
+        return e ? atoi(e) : 31;
     }();
     const uint32_t rows = io.last - io.first;
     const dim3 grid((rows + WALK_BLOCK - 1) / WALK_BLOCK), block(WALK_BLOCK);

@@ -27,7 +27,7 @@ __device__ __forceinline__ uint32_t cell_key(const GridDesc &g, int cx, int cy, 
 }
 __device__ __forceinline__ uint32_t cell_key_of(const GridDesc &g, float4 p) {
     return cell_key(g, cell_coord_x(g, p.x), cell_coord(p.y, g.origin[1], g.inv_cell, g.dim[1]),
-                    cell_coord(p.z, g.origin[2], g.inv_cell, g.dim[2]));
+                    cell_coord(p.z, g.origin[2], g.inv_cell_z, g.dim[2]));
 }
 // The cell a slot was BINNED under (its position may since have drifted by up to skin / 2).
 __device__ __forceinline__ void home_cell(const GridDesc &g, uint32_t key, int &cx, int &cy, int &cz) {

@@ -54,6 +54,11 @@ struct GridDesc {
     int xoff;          // global layer index of local layer 0 (0 on a single GPU)
     float skin;        // cell = reach * (1 + 1/512) + skin: a binning stays exact while every
                        // boid is within skin / 2 of the position it was binned at
+    // Along z (the fastest key dimension, the direction of a walk "row") cells are split into
+    // zspan slices: a boid's row range is cz - zspan .. cz + zspan, i.e. (2 + 1/zspan) cell
+    // edges instead of 3 -- fewer candidates at no extra rows.
+    float inv_cell_z;  // zspan / cell
+    int zspan;         // 1, 2 or 4
 };
 
 // Device-side control block of the lazy re-binning (fp_misc.cu: skin_gate_kernel).

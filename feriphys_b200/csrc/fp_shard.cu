@@ -478,7 +478,7 @@ __global__ void slab_keys_kernel(const GridDesc g, int xs0, int xs1, const float
             // (a flagged stray is kept in the nearest owned layer: ghost layers hold no owned record)
             const int cx = min(max(cell_coord_x(g, p.x), 1), g.dim[0] - 2);
             key = cell_key(g, cx, cell_coord(p.y, g.origin[1], g.inv_cell, g.dim[1]),
-                           cell_coord(p.z, g.origin[2], g.inv_cell, g.dim[2]));
+                           cell_coord(p.z, g.origin[2], g.inv_cell_z, g.dim[2]));
         }
         keys[i] = key;
     }

@@ -7,20 +7,18 @@
 // its threads can reach is ONE contiguous slot interval of the sorted position
 // array, so the CTA stages those nine intervals into shared memory with 1-D
 // TMA bulk copies (cp.async.bulk -> UBLKCP) signalled on an mbarrier: every
-// candidate position is fetched from L2/HBM once per CTA and then re-read ~24
-// times from shared memory.  Each thread then takes its own boid through three
+// candidate position is fetched from L2/HBM once per CTA and then re-read ~20
+// times from shared memory.  Each thread then takes its own boid through two
 // warp-convergent phases:
-//   1. gate   -- every candidate: squared distance (packed FP32, fused) against
-//                m2_cut (1 + 1e-6) -- a superset of the in-range pairs; the
-//                survivors' tile offsets (16 bit) go to a per-thread list in
-//                shared memory;
-//   2. FOV    -- survivors only: a cheap approximate cosine drops pairs that are
-//                CERTAINLY culled (margin 1e-5 >> its 1e-6 error bound); anything
-//                near the threshold is kept for the exact test of phase 3;
-//   3. forces -- remaining pairs: the exact squared distance against m2_cut, then
-//                the exact pair function (pair_inrange, which re-tests the FOV
-//                exactly), accumulated in list (= slot) order.
-// A full list is drained (phases 2+3) before the next chunk, warp-uniformly, and
+//   1. pre-gate -- every candidate, packed FP32 (two candidates per instruction), fused and
+//                approximate on purpose: squared distance against m2_cut (1 + 1e-6) and a
+//                conservative field-of-view test (drops only pairs culled with a 1e-5
+//                margin) -- a superset of the contributing pairs; the survivors' tile
+//                offsets (16 bit) go to a per-thread list in shared memory;
+//   2. forces   -- survivors only: the exact squared distance against m2_cut, then the exact
+//                pair function (which re-tests the FOV exactly), accumulated in list
+//                (= slot) order.
+// A full list is drained (phase 2) before the next chunk, warp-uniformly, and
 // the row loop is kept rolled so the kernel stays inside the instruction cache.
 //
 // Arithmetic and summation order are exactly those of the one-phase kernel
@@ -79,22 +77,8 @@ struct Walk3Smem {
     alignas(8) uint64_t bar;
 };
 
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-// Conservative FOV pre-filter.  c~ is within 1e-6 of the exact cosine of boid.rs:102-105
-// (|vhat| = 1 +- 2e-7, rsqrt.approx and the fused dot are each good to a few ulp), so a
-// pair is dropped only when it is culled with a 1e-5 margin on both sides of the band
-// -1 <= c <= cstar; NaN never drops.  The exact test in pair_inrange has the last word.
-__device__ __forceinline__ bool fov_certainly_culled(const Self &s, V3 d, float m2, float cstar) {
-    const float q = fmaf(s.vhat.z, d.z, fmaf(s.vhat.y, d.y, s.vhat.x * d.x));
-    const float c = q * rsqrtf(m2);
-    return c < cstar - 1e-5f && c > -1.0f + 1e-5f;
-}
-
 template <int TAP, int BLOCK, int TILE_CAP, int CAP, int PH>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 768 / BLOCK)
 grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned *__restrict__ status,
                   TapOut tap) {
     static_assert(TILE_CAP + 8 <= 4096, "list entries carry a 12-bit tile offset");
@@ -141,7 +125,7 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
     // the nine slot ranges of this boid, rows in ascending key order (dx outer, dy inner)
     uint32_t jb[9], je[9];
     {
-        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
+        const int z0 = max(cz - g.zspan, 0), z1 = min(cz + g.zspan, g.dim[2] - 1);
 #pragma unroll
         for (int r = 0; r < 9; ++r) {
             const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
@@ -166,32 +150,40 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        uint32_t total = 0;
-        for (int r = 0; r < 9; ++r) {
-            S.toff[r] = total;
-            if (S.ue[r] > S.ub[r]) {  // 16-byte granules for the 4-byte SoA arrays
-                S.ub[r] &= ~3u;
-                S.ue[r] = (S.ue[r] + 3u) & ~3u;
-                total += S.ue[r] - S.ub[r];
-            } else {
-                S.ub[r] = S.ue[r] = 0;
-            }
+    if (tid < 32) {
+        // warp 0 lays the nine intervals out in the tile (lane r = row r) and issues the copies
+        uint32_t ub = tid < 9 ? S.ub[tid] : 0u, ue = tid < 9 ? S.ue[tid] : 0u;
+        if (ue > ub) {  // 16-byte granules for the 4-byte SoA arrays
+            ub &= ~3u;
+            ue = (ue + 3u) & ~3u;
+        } else {
+            ub = ue = 0u;
         }
-        S.toff[9] = total;
-        for (int r = 0; r < 9; ++r) S.tslot[r] = S.ub[r] - S.toff[r];
-        if (total > (uint32_t)TILE_CAP) {
-            S.fallback = 1;
-        } else if (total > 0) {
-            mbar_expect_tx(&S.bar, total * 12u);
-            for (int r = 0; r < 9; ++r) {
-                const uint32_t len = S.ue[r] - S.ub[r];
-                if (len) {
-                    bulk_g2s(&S.tx[S.toff[r]], sx + S.ub[r], len * 4u, &S.bar);
-                    bulk_g2s(&S.ty[S.toff[r]], sy + S.ub[r], len * 4u, &S.bar);
-                    bulk_g2s(&S.tz[S.toff[r]], sz + S.ub[r], len * 4u, &S.bar);
-                }
-            }
+        const uint32_t len = ue - ub;
+        uint32_t inc = len;  // inclusive prefix sum over the lanes
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+            if ((int)tid >= off) inc += t;
+        }
+        const uint32_t toff = inc - len, total = __shfl_sync(0xffffffffu, inc, 8);
+        if (tid < 9) {
+            S.ub[tid] = ub;
+            S.ue[tid] = ue;
+            S.toff[tid] = toff;
+            S.tslot[tid] = ub - toff;
+        }
+        const bool staged = total > 0 && total <= (uint32_t)TILE_CAP;
+        if (tid == 0) {
+            S.toff[9] = total;
+            if (total > (uint32_t)TILE_CAP) S.fallback = 1;
+            if (staged) mbar_expect_tx(&S.bar, total * 12u);
+        }
+        __syncwarp();
+        if (staged && tid < 9 && len) {
+            bulk_g2s(&S.tx[toff], sx + ub, len * 4u, &S.bar);
+            bulk_g2s(&S.ty[toff], sy + ub, len * 4u, &S.bar);
+            bulk_g2s(&S.tz[toff], sz + ub, len * 4u, &S.bar);
         }
     }
     __syncthreads();
@@ -199,7 +191,7 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
     if (S.fallback) {
         // one-phase walk from global memory (dense cluster: the tile would not fit)
         if (work) {
-            const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
+            const int z0 = max(cz - g.zspan, 0), z1 = min(cz + g.zspan, g.dim[2] - 1);
             for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x) {
                 for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
                     const uint32_t rowbase = row_base(g, x, y);
@@ -236,6 +228,9 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
         // -p_i broadcast into both halves: p_j + (-p_i) == p_j - p_i exactly
         const float2 nsx = make_float2(-self.p.x, -self.p.x), nsy = make_float2(-self.p.y, -self.p.y),
                      nsz = make_float2(-self.p.z, -self.p.z);
+        const float2 vhx = make_float2(self.vhat.x, self.vhat.x), vhy = make_float2(self.vhat.y, self.vhat.y),
+                     vhz = make_float2(self.vhat.z, self.vhat.z);
+        const float2 kh2 = make_float2(P.fov_kh, P.fov_kh), kl2 = make_float2(P.fov_kl, P.fov_kl);
 #pragma unroll 1
         for (int r = 0; r <= 9; ++r) {
             const uint32_t pk = S.rng[r][tid];
@@ -247,76 +242,49 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
                 int room = CAP - (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);
                 const bool more = __any_sync(0xffffffffu, i < len);
                 if (room == 0 || (r == 9 && room < CAP)) {
-                    // phase 2: drop self and the certainly-culled.  Batches of PH: all list and
-                    // tile loads of a batch are issued before its stores (the compiler must
-                    // assume the 16-bit list stores alias the tile), compaction stays in order.
-                    int nb = 0;
-                    for (int k = 0; k < cnt; k += PH) {
-                        uint32_t tt[PH];
-                        V3 pp[PH];
-#pragma unroll
-                        for (int u = 0; u < PH; ++u) tt[u] = lst[min(k + u, cnt - 1) * BLOCK];
-#pragma unroll
-                        for (int u = 0; u < PH; ++u) {
-                            const uint32_t t = tt[u] & 0xfffu;
-                            pp[u] = v3(S.tx[t], S.ty[t], S.tz[t]);
-                        }
-                        bool keep[PH];
-#pragma unroll
-                        for (int u = 0; u < PH; ++u) {
-                            const V3 d = v3(pp[u].x - self.p.x, pp[u].y - self.p.y, pp[u].z - self.p.z);
-                            const float m2 = fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x));
-                            keep[u] = k + u < cnt && (tt[u] & 0xfffu) != t_self &&
-                                      !fov_certainly_culled(self, d, m2, P.cstar);
-                        }
-#pragma unroll
-                        for (int u = 0; u < PH; ++u)
-                            if (keep[u]) {  // survivor: keep it and start pulling its velocity in
-                                lst[(nb++) * BLOCK] = (uint16_t)tt[u];
-                                prefetch_l2(vel_s + ((tt[u] & 0xfffu) + S.tslot[tt[u] >> 12]));
-                            }
-                    }
-                    // phase 3: exact forces in list (= slot) order.  An entry is (row << 12 | tile
+                    // drain: exact forces in list (= slot) order.  An entry is (row << 12 | tile
                     // offset); the row turns the offset back into a slot for the velocity gather.
+                    const int nb = cnt;
                     auto slot_of = [&](uint32_t e) { return (e & 0xfffu) + S.tslot[e >> 12]; };
                     // Two entries per trip: their (branch-free) force evaluations are independent
-                    // and interleave; the two adds into acc stay in list order.
-                    uint32_t t_nx = nb ? lst[0] : 0u;
+                    // and interleave; the two adds into acc stay in list order.  Velocities are
+                    // fetched one trip ahead.
+                    uint32_t t_nx = nb ? lst[0] : 0u, t_nx2 = nb > 1 ? lst[BLOCK] : t_nx;
                     float4 v_nx = nb ? __ldg(vel_s + slot_of(t_nx)) : make_float4(0, 0, 0, 0);
+                    float4 v_nx2 = nb > 1 ? __ldg(vel_s + slot_of(t_nx2)) : v_nx;
                     for (int k = 0; k < nb; k += 2) {
-                        const uint32_t ta = t_nx;
-                        const float4 va = v_nx;
+                        const uint32_t ta = t_nx, tb = t_nx2;
+                        const float4 va = v_nx, vb = v_nx2;
                         const bool hasb = k + 1 < nb;
-                        uint32_t tb = ta;
-                        float4 vb = va;
-                        if (hasb) {
-                            tb = lst[(k + 1) * BLOCK];
-                            vb = __ldg(vel_s + slot_of(tb));
-                        }
                         if (k + 2 < nb) {
                             t_nx = lst[(k + 2) * BLOCK];
+                            t_nx2 = k + 3 < nb ? lst[(k + 3) * BLOCK] : t_nx;
                             v_nx = __ldg(vel_s + slot_of(t_nx));
+                            v_nx2 = __ldg(vel_s + slot_of(t_nx2));
                         }
                         const uint32_t ia = ta & 0xfffu, ib = tb & 0xfffu;
                         const V3 pa = v3(S.tx[ia], S.ty[ia], S.tz[ia]), pb = v3(S.tx[ib], S.ty[ib], S.tz[ib]);
                         V3 da, db;
                         const float ma = pair_m2(self, v3(pa.x, pa.y, pa.z), da);
                         const float mb = pair_m2(self, v3(pb.x, pb.y, pb.z), db);
-                        const bool fast = P.fast_ok && ma >= FAST_M2_LO && ma <= FAST_M2_HI &&
-                                          mb >= FAST_M2_LO && mb <= FAST_M2_HI;
-                        if (fast) {
+                        // what counts: not the boid itself (flocking.rs:137-139), and in range by the
+                        // EXACT squared distance (the pre-gate let a sliver too many through)
+                        const bool oka = ia != t_self && !(ma >= P.m2_cut);
+                        const bool okb = hasb && ib != t_self && !(mb >= P.m2_cut);
+                        const bool fast = P.fast_ok && (!oka || (ma >= FAST_M2_LO && ma <= FAST_M2_HI)) &&
+                                          (!okb || (mb >= FAST_M2_LO && mb <= FAST_M2_HI));
+                        if (fast) {  // (a lane that does not count may hold inf / NaN; it is never used)
                             bool visa, visb;
                             const V3 fa = pair_force_fast(P, self, da, ma, v3(va.x, va.y, va.z), visa);
                             const V3 fb = pair_force_fast(P, self, db, mb, v3(vb.x, vb.y, vb.z), visb);
-                            // (exact distance gate: the pre-gate of phase 1 let a sliver too many through)
-                            if (visa && !(ma >= P.m2_cut)) acc = vadd(acc, fa);
-                            if (hasb && visb && !(mb >= P.m2_cut)) acc = vadd(acc, fb);
+                            if (oka && visa) acc = vadd(acc, fa);
+                            if (okb && visb) acc = vadd(acc, fb);
                         } else {  // extreme distances (coincident boids, ...): generic exact path
                             V3 contrib;
-                            if (!(ma >= P.m2_cut) &&
+                            if (oka &&
                                 pair_inrange<false>(P, self, da, ma, v3(va.x, va.y, va.z), 1.0f, P.cstar, contrib))
                                 acc = vadd(acc, contrib);
-                            if (hasb && !(mb >= P.m2_cut) &&
+                            if (okb &&
                                 pair_inrange<false>(P, self, db, mb, v3(vb.x, vb.y, vb.z), 1.0f, P.cstar, contrib))
                                 acc = vadd(acc, contrib);
                         }
@@ -333,9 +301,14 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
                 const uint32_t tag = (uint32_t)r << 12;
                 // Batches of four candidates at an even tile index: two neighbours load as one
                 // 64-bit pair and go through the packed FP32 pipe (FADD2 / FMUL2 / FFMA2, sm_100).
-                // This is a PRE-gate: the fused sum of squares is within 4e-7 relative of the
-                // reference's separately rounded one, so keeping everything below m2_cut_hi =
-                // m2_cut (1 + 1e-6) keeps a superset; phase 3 re-tests the exact m2 against m2_cut.
+                // This is a PRE-gate, deliberately fused and approximate -- it only has to keep a
+                // superset of the pairs that contribute; the drain re-tests exactly:
+                //  * distance: the fused sum of squares is within 4e-7 relative of the reference's
+                //    separately rounded one; everything below m2_cut_hi = m2_cut (1 + 1e-6) stays;
+                //  * field of view: c~ = q / sqrt(m2), q = vhat . d, is within 1e-6 of the exact
+                //    cosine (boid.rs:102-105); a pair is dropped only when it is culled with a 1e-5
+                //    margin, -1 + 1e-5 < c~ < cstar - 1e-5, tested without the square root through
+                //    the monotone map x -> x |x|:  KL m2 < q |q| < KH m2.  NaN never drops.
                 auto gate4 = [&](uint32_t T, uint32_t live) {  // live: bit u set <=> candidate T+u counts
                     const float2 x01 = *reinterpret_cast<const float2 *>(&S.tx[T]);
                     const float2 x23 = *reinterpret_cast<const float2 *>(&S.tx[T + 2]);
@@ -348,10 +321,19 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
                     const float2 dz01 = __fadd2_rn(z01, nsz), dz23 = __fadd2_rn(z23, nsz);
                     const float2 m01 = __ffma2_rn(dz01, dz01, __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01)));
                     const float2 m23 = __ffma2_rn(dz23, dz23, __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23)));
+                    const float2 q01 = __ffma2_rn(vhz, dz01, __ffma2_rn(vhy, dy01, __fmul2_rn(vhx, dx01)));
+                    const float2 q23 = __ffma2_rn(vhz, dz23, __ffma2_rn(vhy, dy23, __fmul2_rn(vhx, dx23)));
+                    const float2 s01 = __fmul2_rn(q01, make_float2(fabsf(q01.x), fabsf(q01.y)));
+                    const float2 s23 = __fmul2_rn(q23, make_float2(fabsf(q23.x), fabsf(q23.y)));
+                    const float2 h01 = __fmul2_rn(kh2, m01), h23 = __fmul2_rn(kh2, m23);
+                    const float2 l01 = __fmul2_rn(kl2, m01), l23 = __fmul2_rn(kl2, m23);
                     const float mm[4] = {m01.x, m01.y, m23.x, m23.y};
+                    const float ss[4] = {s01.x, s01.y, s23.x, s23.y};
+                    const float hh[4] = {h01.x, h01.y, h23.x, h23.y};
+                    const float ll[4] = {l01.x, l01.y, l23.x, l23.y};
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if ((live >> u & 1u) && !(mm[u] >= P.m2_cut_hi)) {
+                        if ((live >> u & 1u) && !(mm[u] >= P.m2_cut_hi) && !(ss[u] < hh[u] && ss[u] > ll[u])) {
                             lst[w] = (uint16_t)(tag | (T + u));
                             w += BLOCK;
                         }
@@ -393,14 +375,14 @@ int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, in
     return tap == TAP_STEP ? launch3<TAP_STEP, B, T, C, H>(st, P, g, io, status, tap_out) \
                            : launch3<TAP_ACCEL, B, T, C, H>(st, P, g, io, status, tap_out)
     switch (variant) {
-        case 31: FP_W3(128, 2048, 64, 4);   // 46 KB: 4 CTAs / SM
-        case 32: FP_W3(128, 1792, 64, 4);   // 43 KB: 5 CTAs / SM
-        case 33: FP_W3(128, 1536, 48, 4);   // 36 KB: 6 CTAs / SM
-        case 34: FP_W3(128, 1664, 48, 4);   // 37 KB: 5-6 CTAs / SM
-        case 35: FP_W3(128, 1792, 56, 4);   // 41 KB: 5 CTAs / SM
-        case 36: FP_W3(64, 1024, 64, 4);    // 23 KB: 9 CTAs / SM
-        case 37: FP_W3(64, 1024, 48, 4);    // 21 KB: 10 CTAs / SM
-        default: FP_W3(128, 1792, 64, 4);
+        case 31: FP_W3(128, 1792, 64, 4);   // 43 KB: 5 CTAs / SM
+        case 32: FP_W3(128, 1792, 40, 4);   // 37 KB: 6 CTAs / SM
+        case 33: FP_W3(128, 1792, 56, 4);   // 41 KB: 5 CTAs / SM
+        case 34: FP_W3(128, 1792, 48, 4);   // 39 KB: 5 CTAs / SM
+        case 35: FP_W3(128, 1792, 80, 4);   // 47 KB: 4 CTAs / SM
+        case 36: FP_W3(128, 1536, 64, 4);   // 40 KB: 5 CTAs / SM
+        case 37: FP_W3(64, 1024, 64, 4);    // 23 KB: 9 CTAs / SM
+        default: FP_W3(128, 1792, 64, 4);   // one drain per boid almost always: lists average 17 entries
     }
 #undef FP_W3
 }
