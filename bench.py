@@ -300,6 +300,8 @@ def config_block(w, args, world):
 
 # ---- our arm -----------------------------------------------------------------------------
 def run_ours(args, w, rank, world, local_rank):
+    from ctypes import byref, c_uint64 as C_uint64
+
     import torch
     from feriphys_b200 import _lib
     from feriphys_b200.flocking import Simulation, Obstacle, PointAttractor, BoundingBox
@@ -360,6 +362,16 @@ def run_ours(args, w, rank, world, local_rank):
         ll = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(ll)
         launches = int(ll[0])
+        # sanity of the sharded run: every boid owned by exactly one rank, no capacity / halo /
+        # slab-jump / barrier flags raised on any rank
+        own = C_uint64()
+        _lib.check(lib.fp_flock_local_len(sim._h, byref(own)))
+        bad = int(sim.status()) & ~3        # (bits 1 | 2: steering terms the reference would panic on)
+        chk = torch.tensor([int(own.value), 1 if bad else 0], device="cuda", dtype=torch.int64)
+        dist.all_reduce(chk)
+        if int(chk[0]) != n or int(chk[1]):
+            raise SystemExit(f"sharded run inconsistent: {int(chk[0])} boids owned of {n}, "
+                             f"{int(chk[1])} ranks raised capacity/halo/barrier flags (this rank: {bad})")
     value = n * K / dev_s
 
     # ---- e2e: the drop-in call sequence with HOST buffers, copies inside the timed region

@@ -10,6 +10,8 @@
 // FP32-pipe bound: per ordered pair 8 flops when rejected by
 // distance, 18 when FOV-culled, 54 when it contributes.  State is 32 B/boid
 // and is re-read from shared memory N times, so HBM traffic is negligible.
+#include <stdlib.h>
+
 #include "fp_internal.h"
 
 namespace fp {
@@ -130,17 +132,199 @@ allpairs_kernel(const DevParams P, const float4 *__restrict__ pos_all,
     if (flags) atomicOr(status, flags);
 }
 
+// ---- production form for TAP_STEP / TAP_ACCEL: staged tiles, packed pre-gate, list, drain ----
+// Same structure as the staged grid walk (fp_walk.cu): a tile of AP2_TJ candidates is staged in
+// shared memory (positions SoA, velocities float4); every thread runs the packed, fused
+// PRE-gate over the tile -- squared distance against m2_cut (1 + 1e-6) and the conservative
+// field-of-view filter, two candidates per FP32 instruction, a superset of the contributing
+// pairs -- and appends the survivors' tile offsets to its list; the list is then drained with
+// the EXACT distance test and the exact pair function, in ascending j.  A batch of four
+// candidates none of which is in range (the common case in a sparse flock) costs 6 shared
+// loads, 12 packed operations and one branch.  Bit-identical to allpairs_kernel.
+constexpr int AP2_TJ = 128;   // candidates per tile; also the list capacity (all may survive)
+
+struct Ap2Smem {
+    alignas(16) float tx[AP2_TJ], ty[AP2_TJ], tz[AP2_TJ];
+    float4 tv[AP2_TJ];
+    uint16_t list[AP2_TJ][AP_BLOCK];  // [entry][thread]: bank == lane
+};
+
+template <int TAP>
+__global__ void __launch_bounds__(AP_BLOCK, 5)
+allpairs2_kernel(const DevParams P, const float4 *__restrict__ pos_all,
+                 const float4 *__restrict__ vel_all, uint32_t n_all, uint32_t row0, uint32_t nrows,
+                 float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
+                 unsigned *__restrict__ status, TapOut tap) {
+    extern __shared__ __align__(16) unsigned char ap2_raw[];
+    Ap2Smem &S = *reinterpret_cast<Ap2Smem *>(ap2_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t r = blockIdx.x * AP_BLOCK + tid;
+    const bool active = r < nrows;
+    const uint32_t i = row0 + (active ? r : 0);
+    const float4 pi4 = __ldg(pos_all + i);
+    const float4 vi4 = __ldg(vel_all + i);
+    const Self self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
+    V3 acc = v3zero();
+    const bool need_pairs = (TAP != TAP_STEP) || !P.steering_overrides;
+    if (need_pairs) {
+        const float2 nsx = make_float2(-self.p.x, -self.p.x), nsy = make_float2(-self.p.y, -self.p.y),
+                     nsz = make_float2(-self.p.z, -self.p.z);
+        const float2 vhx = make_float2(self.vhat.x, self.vhat.x), vhy = make_float2(self.vhat.y, self.vhat.y),
+                     vhz = make_float2(self.vhat.z, self.vhat.z);
+        const float2 kh2 = make_float2(P.fov_kh, P.fov_kh), kl2 = make_float2(P.fov_kl, P.fov_kl);
+        uint16_t *const lst = &S.list[0][tid];
+        for (uint32_t j0 = 0; j0 < n_all; j0 += AP2_TJ) {
+            const uint32_t jl = j0 + tid;
+            float4 pj = make_float4(0, 0, 0, 0), vj = pj;
+            if (jl < n_all) {
+                pj = __ldg(pos_all + jl);
+                vj = __ldg(vel_all + jl);
+            }
+            __syncthreads();  // the previous tile has been drained by everyone
+            S.tx[tid] = pj.x;
+            S.ty[tid] = pj.y;
+            S.tz[tid] = pj.z;
+            S.tv[tid] = vj;
+            __syncthreads();
+            const uint32_t cnt = min((uint32_t)AP2_TJ, n_all - j0);
+            const uint32_t t_self = (i >= j0 && i < j0 + cnt) ? i - j0 : 0xffffu;
+            uint32_t w = 0;  // list cursor, in entries * AP_BLOCK
+            if (active) {
+#pragma unroll 2
+                for (uint32_t T = 0; T < cnt; T += 4) {
+                    const float2 x01 = *reinterpret_cast<const float2 *>(&S.tx[T]);
+                    const float2 x23 = *reinterpret_cast<const float2 *>(&S.tx[T + 2]);
+                    const float2 y01 = *reinterpret_cast<const float2 *>(&S.ty[T]);
+                    const float2 y23 = *reinterpret_cast<const float2 *>(&S.ty[T + 2]);
+                    const float2 z01 = *reinterpret_cast<const float2 *>(&S.tz[T]);
+                    const float2 z23 = *reinterpret_cast<const float2 *>(&S.tz[T + 2]);
+                    const float2 dx01 = __fadd2_rn(x01, nsx), dx23 = __fadd2_rn(x23, nsx);
+                    const float2 dy01 = __fadd2_rn(y01, nsy), dy23 = __fadd2_rn(y23, nsy);
+                    const float2 dz01 = __fadd2_rn(z01, nsz), dz23 = __fadd2_rn(z23, nsz);
+                    const float2 m01 = __ffma2_rn(dz01, dz01, __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01)));
+                    const float2 m23 = __ffma2_rn(dz23, dz23, __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23)));
+                    const float mm[4] = {m01.x, m01.y, m23.x, m23.y};
+                    bool near[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) near[u] = T + u < cnt && !(mm[u] >= P.m2_cut_hi);
+                    if (near[0] | near[1] | near[2] | near[3]) {
+                        const float2 q01 = __ffma2_rn(vhz, dz01, __ffma2_rn(vhy, dy01, __fmul2_rn(vhx, dx01)));
+                        const float2 q23 = __ffma2_rn(vhz, dz23, __ffma2_rn(vhy, dy23, __fmul2_rn(vhx, dx23)));
+                        const float2 s01 = __fmul2_rn(q01, make_float2(fabsf(q01.x), fabsf(q01.y)));
+                        const float2 s23 = __fmul2_rn(q23, make_float2(fabsf(q23.x), fabsf(q23.y)));
+                        const float2 h01 = __fmul2_rn(kh2, m01), h23 = __fmul2_rn(kh2, m23);
+                        const float2 l01 = __fmul2_rn(kl2, m01), l23 = __fmul2_rn(kl2, m23);
+                        const float ss[4] = {s01.x, s01.y, s23.x, s23.y};
+                        const float hh[4] = {h01.x, h01.y, h23.x, h23.y};
+                        const float ll[4] = {l01.x, l01.y, l23.x, l23.y};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (near[u] && !(ss[u] < hh[u] && ss[u] > ll[u])) {
+                                lst[w] = (uint16_t)(T + u);
+                                w += AP_BLOCK;
+                            }
+                    }
+                }
+            }
+            // drain: exact distance, exact pair function, ascending j; two entries per trip
+            const int nb = (int)(w / AP_BLOCK);
+            if (__any_sync(0xffffffffu, nb > 0)) {
+                for (int k = 0; k < nb; k += 2) {
+                    const bool hasb = k + 1 < nb;
+                    const uint32_t ia = lst[k * AP_BLOCK], ib = hasb ? lst[(k + 1) * AP_BLOCK] : ia;
+                    const float4 va = S.tv[ia], vb = S.tv[ib];
+                    V3 da, db;
+                    const float ma = pair_m2(self, v3(S.tx[ia], S.ty[ia], S.tz[ia]), da);
+                    const float mb = pair_m2(self, v3(S.tx[ib], S.ty[ib], S.tz[ib]), db);
+                    const bool oka = ia != t_self && !(ma >= P.m2_cut);
+                    const bool okb = hasb && ib != t_self && !(mb >= P.m2_cut);
+                    const bool fast = P.fast_ok && (!oka || (ma >= FAST_M2_LO && ma <= FAST_M2_HI)) &&
+                                      (!okb || (mb >= FAST_M2_LO && mb <= FAST_M2_HI));
+                    if (fast) {  // (a lane that does not count may hold inf / NaN; it is never used)
+                        bool visa, visb;
+                        const V3 fa = pair_force_fast(P, self, da, ma, v3(va.x, va.y, va.z), visa);
+                        const V3 fb = pair_force_fast(P, self, db, mb, v3(vb.x, vb.y, vb.z), visb);
+                        if (oka && visa) acc = vadd(acc, fa);
+                        if (okb && visb) acc = vadd(acc, fb);
+                    } else {
+                        V3 contrib;
+                        if (oka && pair_inrange<false>(P, self, da, ma, v3(va.x, va.y, va.z), 1.0f, P.cstar, contrib))
+                            acc = vadd(acc, contrib);
+                        if (okb && pair_inrange<false>(P, self, db, mb, v3(vb.x, vb.y, vb.z), 1.0f, P.cstar, contrib))
+                            acc = vadd(acc, contrib);
+                    }
+                }
+            }
+        }
+    }
+    if (!active) return;
+    const uint32_t idx = __float_as_uint(pi4.w);  // caller index
+    Extras e;
+    unsigned flags = 0;
+    const V3 a = accel_total(P, self, acc, e, flags, TAP == TAP_ACCEL);
+    if (TAP == TAP_ACCEL) {
+        float *o = tap.accel3 + 3ull * idx;
+        o[0] = a.x; o[1] = a.y; o[2] = a.z;
+        if (tap.comp15) {
+            float *c = tap.comp15 + 15ull * idx;
+            c[0] = acc.x; c[1] = acc.y; c[2] = acc.z;
+            c[3] = e.lead.x; c[4] = e.lead.y; c[5] = e.lead.z;
+            c[6] = e.attr.x; c[7] = e.attr.y; c[8] = e.attr.z;
+            c[9] = e.bbox.x; c[10] = e.bbox.y; c[11] = e.bbox.z;
+            c[12] = e.steer.x; c[13] = e.steer.y; c[14] = e.steer.z;
+        }
+        if (flags) atomicOr(status, flags);
+        return;
+    }
+    V3 np, nv;
+    euler(P, self.p, self.v, a, np, nv);
+    pos_out[r] = make_float4(np.x, np.y, np.z, pi4.w);
+    vel_out[r] = make_float4(nv.x, nv.y, nv.z, 0.0f);
+    if (flags) atomicOr(status, flags);
+}
+
+template <int TAP>
+static int launch_ap2(cudaStream_t st, const dim3 grid, const DevParams &P, const float4 *pos_all,
+                      const float4 *vel_all, uint32_t n_all, uint32_t row0, uint32_t nrows, float4 *pos_out,
+                      float4 *vel_out, unsigned *status, const TapOut &tap_out) {
+    auto kern = allpairs2_kernel<TAP>;
+    const int smem = (int)sizeof(Ap2Smem);
+    FP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, AP_BLOCK, smem, st>>>(P, pos_all, vel_all, n_all, row0, nrows, pos_out, vel_out, status, tap_out);
+    return FP_OK;
+}
+
 int launch_allpairs(cudaStream_t st, const DevParams &P, int tap, const float4 *pos_all,
                     const float4 *vel_all, uint32_t n_all, uint32_t row0, uint32_t nrows,
-                    float4 *pos_out, float4 *vel_out, unsigned *status, const TapOut &tap_out) {
+                    float4 *pos_out, float4 *vel_out, unsigned *status, const TapOut &tap_out, int variant) {
     if (nrows == 0) return FP_OK;
     const dim3 grid((nrows + AP_BLOCK - 1) / AP_BLOCK), block(AP_BLOCK);
+    // variant 0: staged (pre-gate + lists; wins when most pairs are out of range), 1: one-phase
+    // (wins in dense flocks where most candidates contribute).  Same bits either way; the
+    // handle times both and keeps the faster.  FP_ALLPAIRS_VARIANT=0|1 pins one (debug).
+    static const int pinned = [] {
+        const char *e = getenv("FP_ALLPAIRS_VARIANT");
+        return e && *e ? atoi(e) : -1;
+    }();
+    const bool staged = (pinned >= 0 ? pinned : variant) == 0;
     switch (tap) {
         case TAP_STEP:
+            if (staged) {
+                int rc = launch_ap2<TAP_STEP>(st, grid, P, pos_all, vel_all, n_all, row0, nrows, pos_out, vel_out,
+                                              status, tap_out);
+                if (rc) return rc;
+                break;
+            }
             allpairs_kernel<TAP_STEP><<<grid, block, 0, st>>>(P, pos_all, vel_all, n_all, row0, nrows,
                                                               pos_out, vel_out, status, tap_out);
             break;
         case TAP_ACCEL:
+            if (staged) {
+                int rc = launch_ap2<TAP_ACCEL>(st, grid, P, pos_all, vel_all, n_all, row0, nrows, pos_out, vel_out,
+                                               status, tap_out);
+                if (rc) return rc;
+                break;
+            }
             allpairs_kernel<TAP_ACCEL><<<grid, block, 0, st>>>(P, pos_all, vel_all, n_all, row0, nrows,
                                                                pos_out, vel_out, status, tap_out);
             break;

@@ -559,6 +559,41 @@ int64_t flock_plan_steps(const fp_flock *f, float D, float first_delta) { return
 float flock_plan_delta(float v2max, float pmax, float dt) { return plan_delta(v2max, pmax, dt); }
 }  // namespace fp
 
+namespace fp {
+int flock_allpairs_step(fp_flock *f, const float4 *pos_all, const float4 *vel_all, uint32_t n_all, uint32_t row0,
+                        uint32_t nrows, float4 *pos_out, float4 *vel_out) {
+    if (f->ap_choice >= 0 && ++f->ap_age >= 1024) {  // the flock may have changed density: measure again
+        f->ap_choice = -1;
+        f->ap_probe = 0;
+    }
+    int variant = f->ap_choice;
+    int probing = -1;
+    if (variant < 0) {
+        if (f->ap_probe == 2) {  // both timings are in flight: wait for them once and decide
+            float t0 = 0, t1 = 0;
+            FP_CUDA(cudaEventSynchronize(f->ap_ev[3]));
+            FP_CUDA(cudaEventElapsedTime(&t0, f->ap_ev[0], f->ap_ev[1]));
+            FP_CUDA(cudaEventElapsedTime(&t1, f->ap_ev[2], f->ap_ev[3]));
+            f->ap_choice = variant = t1 < t0 ? 1 : 0;
+            f->ap_age = 0;
+        } else {
+            probing = variant = (int)f->ap_probe;
+            for (auto &e : f->ap_ev)
+                if (!e) FP_CUDA(cudaEventCreate(&e));
+            FP_CUDA(cudaEventRecord(f->ap_ev[2 * probing], f->stream));
+        }
+    }
+    int rc = launch_allpairs(f->stream, f->P, TAP_STEP, pos_all, vel_all, n_all, row0, nrows, pos_out, vel_out,
+                             f->d_status, TapOut{}, variant);
+    if (rc) return rc;
+    if (probing >= 0) {
+        FP_CUDA(cudaEventRecord(f->ap_ev[2 * probing + 1], f->stream));
+        ++f->ap_probe;
+    }
+    return FP_OK;
+}
+}  // namespace fp
+
 // ---- C ABI ----------------------------------------------------------------------
 extern "C" {
 
@@ -677,6 +712,7 @@ int fp_flock_destroy(fp_flock *f) {
     if (f->d_stage) cudaFree(f->d_stage);
     if (f->h_ctl) cudaFreeHost(f->h_ctl);
     for (auto &ev : f->ev_pool) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : f->ap_ev) if (ev) cudaEventDestroy(ev);
     if (f->stream) cudaStreamDestroy(f->stream);
     delete f;
     return FP_OK;
@@ -693,6 +729,8 @@ int fp_flock_set_config(fp_flock *f, const fp_config *cfg) {
     derive_params(f->cfg, f->P);
     if (reach_of(f->cfg) != old_reach) f->grid_valid = false;
     f->bin_valid = false;  // dt and reach enter the skin accounting
+    f->ap_choice = -1;     // a new reach changes which all-pairs kernel wins
+    f->ap_probe = 0;
     return FP_OK;
 }
 
@@ -878,8 +916,8 @@ int fp_flock_step(fp_flock *f, uint32_t nsteps) {
         rc = ensure_caller_order(f);
         if (rc) return rc;
         if ((rc = mark(f))) return rc;
-        rc = launch_allpairs(f->stream, f->P, TAP_STEP, f->pos[f->cur], f->vel[f->cur], f->n, 0,
-                             f->n, f->pos[f->cur ^ 1], f->vel[f->cur ^ 1], f->d_status, TapOut{});
+        rc = flock_allpairs_step(f, f->pos[f->cur], f->vel[f->cur], f->n, 0, f->n, f->pos[f->cur ^ 1],
+                                 f->vel[f->cur ^ 1]);
         if (rc) return rc;
         f->cur ^= 1;
         if ((rc = mark(f))) return rc;

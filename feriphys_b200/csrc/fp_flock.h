@@ -60,5 +60,10 @@ struct fp_flock {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     bool timing = false;
+    // all-pairs kernel choice (staged / one-phase: bit-identical, speed depends on density):
+    // steps 0 and 1 after a (re)start are timed, one kernel each, then the faster one is kept
+    int ap_choice = -1;
+    uint32_t ap_probe = 0, ap_age = 0;
+    cudaEvent_t ap_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     fp::Shard *shard = nullptr;  // multi-GPU state (fp_shard.cu)
 };

@@ -117,7 +117,7 @@ struct WalkIO {
 // pos_all/vel_all.  For TAP_STEP writes pos_out/vel_out[0..nrows).
 int launch_allpairs(cudaStream_t st, const DevParams &P, int tap, const float4 *pos_all,
                     const float4 *vel_all, uint32_t n_all, uint32_t row0, uint32_t nrows,
-                    float4 *pos_out, float4 *vel_out, unsigned *status, const TapOut &tap_out);
+                    float4 *pos_out, float4 *vel_out, unsigned *status, const TapOut &tap_out, int variant = 0);
 
 // One CTA, `nsteps` steps in one launch, reference summation order (fp_small.cu).
 // lead_table: nsteps rows of n_leads x 8 floats, or NULL to use P.leads for every step.

@@ -1107,9 +1107,8 @@ int shard_step(Shard *s, fp_flock *f, uint32_t nsteps) {
         flock_select_leads(f);
         if ((rc = flock_mark(f)) || (rc = flock_mark(f))) return rc;
         const int a = s->acur;
-        rc = launch_allpairs(f->stream, f->P, TAP_STEP, s->all_pos[a], s->all_vel[a], (uint32_t)s->n_global,
-                             s->first, s->n_slice, s->all_pos[a ^ 1] + off, s->all_vel[a ^ 1] + off, f->d_status,
-                             TapOut{});
+        rc = flock_allpairs_step(f, s->all_pos[a], s->all_vel[a], (uint32_t)s->n_global, s->first, s->n_slice,
+                                 s->all_pos[a ^ 1] + off, s->all_vel[a ^ 1] + off);
         if (rc) return rc;
         if ((rc = flock_mark(f))) return rc;
         FP_NCCL(s, s->api.GroupStart());

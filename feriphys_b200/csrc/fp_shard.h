@@ -9,6 +9,9 @@ namespace fp {
 int flock_fit_grid(fp_flock *f);
 void flock_select_leads(fp_flock *f);
 int flock_mark(fp_flock *f);  // timing-hook event
+// one all-pairs step launch with the staged / one-phase choice made by measurement
+int flock_allpairs_step(fp_flock *f, const float4 *pos_all, const float4 *vel_all, uint32_t n_all, uint32_t row0,
+                        uint32_t nrows, float4 *pos_out, float4 *vel_out);
 int64_t flock_plan_steps(const fp_flock *f, float D, float first_delta);
 float flock_plan_delta(float v2max, float pmax, float dt);
 

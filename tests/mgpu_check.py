@@ -165,6 +165,24 @@ def lazy_slabs(orc, c, rank, world, local, nt):
               f"{rebins} binnings / 60 steps, 60-step err {err:.1e}, neighbour sets exact", flush=True)
     assert sim.status() == 0
 
+    # a long run crosses the collective re-fit every 256 steps (slabs re-cut, peer buffers re-mapped)
+    st3 = synth.uniform_flock(30000, 300.0, seed=84)
+    sim, sc = make(st3, _lib.METHOD_GRID, c, None, local)
+    sim.step_many(280)
+    got = sim.read_state()
+    gc, gh = sim.read_neighbors()
+    assert sim.rebin_info()[1] == 280 and sim.status() == 0
+    if rank == 0:
+        cur = st3
+        for _ in range(280):
+            cur, _ = orc.step(c, sc, cur, threads=nt, grid=True)
+        scale = np.maximum(1.0, np.linalg.norm(cur[:, :3], axis=1))
+        err = (np.linalg.norm(got[:, :3] - cur[:, :3], axis=1) / scale).max()
+        assert err <= 1e-4, err
+        rc, rh, _ = orc.neighbors_rows(c, got, threads=nt, grid=True)
+        assert np.array_equal(gc, rc) and np.array_equal(gh, rh), "slab neighbour sets after a re-fit"
+        print(f"[mgpu x{world}] 280 steps across a re-fit: err {err:.1e}, neighbour sets exact", flush=True)
+
     # the plan is 50x too optimistic while an attractor speeds the flock up: every rank must void
     # the same step on the device and replay it after a fresh (collective) binning
     tables = dict(attractors=np.array([[-60, 190, 190, 2.0e4]], f32))
