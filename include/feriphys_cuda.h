@@ -59,8 +59,9 @@ enum {
 #define FP_STATUS_STEER_NAN_OVF 2u  /* Duration::from_secs_f32(NaN / overflow) */
 /* Sharded (multi-GPU) grid runs only; any of these means the step was NOT exact: */
 #define FP_STATUS_SLAB_CAPACITY 4u  /* a rank's slab outgrew its buffers */
-#define FP_STATUS_HALO_OVERFLOW 8u  /* a face message outgrew the halo buffer */
-#define FP_STATUS_SLAB_JUMP 16u     /* a boid crossed more than one cell layer in one step */
+#define FP_STATUS_HALO_OVERFLOW 8u  /* more boids changed slab between two binnings than a message holds */
+#define FP_STATUS_SLAB_JUMP 16u     /* a boid crossed more than one slab between two binnings */
+#define FP_STATUS_PEER_TIMEOUT 32u  /* a rank never posted its step in the device-side barrier */
 
 typedef struct fp_flock fp_flock; /* opaque; owns all device memory */
 
