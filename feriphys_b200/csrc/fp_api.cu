@@ -236,10 +236,17 @@ int fit_grid(fp_flock *f) {
     }
     // Lazy re-binning: a binning stays exact while every boid is within skin / 2 of where it
     // was binned, at the price of (1 + skin / reach)^3 more candidates.  The skin that balances
-    // the two for this flock's speed: skin = sqrt(0.29 * delta * reach), delta = the
-    // per-step displacement bound.  Flocks too fast for three steps per binning get none.
+    // the two for this flock's speed: skin = sqrt(1.9 * (binning cost / step cost) * delta * reach)
+    // (DESIGN.md 4.1), delta = the per-step displacement bound.  Flocks too fast for two steps
+    // per binning get none.
     const float delta = plan_delta(v2max, pmax, f->cfg.dt);
-    float skin = std::min(sqrtf(0.29f * delta * reach), reach / 8.0f);
+    // cost ratio binning : step.  Both grow with the boids a GPU holds (0.15 measured at C4), but
+    // a binning also has a fixed part -- ~20 launches, and on a sharded flock four NCCL groups
+    // and three host syncs (~1.5 ms measured at 8 GPUs) -- that a small or sharded flock
+    // amortises over more steps with a larger skin.
+    const double n_here = std::max<double>(1.0, f->shard ? (double)f->n_global / shard_world(f->shard) : f->n);
+    const double ratio = 0.15 + (f->shard ? 1.5e-3 : 1.0e-4) / (n_here * 0.34e-9);
+    float skin = std::min(sqrtf((float)(1.9 * ratio) * delta * reach), reach / 8.0f);
     if (!(skin > 0.0f) || !std::isfinite(skin) || skin / 2.0f / delta < 2.0f) skin = 0.0f;
     {
         static const char *env = getenv("FP_SKIN");  // tuning: "0" disables, else a fixed skin

@@ -222,6 +222,8 @@ void shard_destroy(Shard *s) {
 }
 
 
+int shard_world(const Shard *s) { return s->world; }
+
 void shard_info(const Shard *s, int *rank, int *world, int *peer_mapped) {
     if (rank) *rank = s->rank;
     if (world) *world = s->world;

@@ -22,6 +22,7 @@ void shard_destroy(Shard *s);
 int shard_method(Shard *s, int requested, const fp_config &cfg);
 int shard_reduce_bounds(Shard *s, cudaStream_t st, float lo[3], float hi[3], float *v2max);
 int shard_settle(Shard *s, fp_flock *f);
+int shard_world(const Shard *s);
 void shard_info(const Shard *s, int *rank, int *world, int *peer_mapped);
 // called by fit_grid once the GLOBAL grid is known: lay out this rank's slab
 int shard_grid_fitted(Shard *s, fp_flock *f);
