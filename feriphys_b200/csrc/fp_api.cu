@@ -242,10 +242,11 @@ int fit_grid(fp_flock *f) {
     const float delta = plan_delta(v2max, pmax, f->cfg.dt);
     // cost ratio binning : step.  Both grow with the boids a GPU holds (0.15 measured at C4), but
     // a binning also has a fixed part -- ~20 launches, and on a sharded flock four NCCL groups
-    // and three host syncs (~1.5 ms measured at 8 GPUs) -- that a small or sharded flock
-    // amortises over more steps with a larger skin.
+    // and three host syncs (0.5 ms fits the 8-GPU measurements: skin 0.11 / 0.25 / 0.42 gave
+    // 0.798 / 0.772 / 0.791 ms per step) -- that a small or sharded flock amortises over more
+    // steps with a larger skin.
     const double n_here = std::max<double>(1.0, f->shard ? (double)f->n_global / shard_world(f->shard) : f->n);
-    const double ratio = 0.15 + (f->shard ? 1.5e-3 : 1.0e-4) / (n_here * 0.34e-9);
+    const double ratio = 0.15 + (f->shard ? 0.5e-3 : 1.0e-4) / (n_here * 0.34e-9);
     float skin = std::min(sqrtf((float)(1.9 * ratio) * delta * reach), reach / 8.0f);
     if (!(skin > 0.0f) || !std::isfinite(skin) || skin / 2.0f / delta < 2.0f) skin = 0.0f;
     {

@@ -188,7 +188,7 @@ def lazy_slabs(orc, c, rank, world, local, nt):
     # the same step on the device and replay it after a fresh (collective) binning
     tables = dict(attractors=np.array([[-60, 190, 190, 2.0e4]], f32))
     sim, sc = make(st, _lib.METHOD_GRID, c, tables, local)
-    sim.set_rebin(skin=-1.0, plan_scale=50.0)
+    sim.set_rebin(skin=0.1, plan_scale=50.0)
     sim.step_many(80)
     got = sim.read_state()
     skin, steps, rebins, replayed = sim.rebin_info()
