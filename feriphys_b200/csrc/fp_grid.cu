@@ -5,11 +5,16 @@
 // restricting each boid to the 27 cells around it is EXACT provided the cell
 // edge exceeds that reach: the same f32 predicates decide the same pairs.
 //
-// Per step: cell keys + per-cell counts -> exclusive scan (cell_start) ->
-// stable radix sort of (key, slot) -> gather into sorted SoA -> 27-cell walk
-// fused with lead/attractor/bbox/steering terms and the Euler update.  The
-// state stays in sorted order between steps (pos.w carries the caller index),
-// so every global access of the next step is coalesced.
+// A BINNING: cell keys + per-cell counts -> exclusive scan (cell_start) -> stable
+// radix sort of (key, slot) -> gather into sorted float4 + SoA arrays.  A STEP:
+// the walk over the 27 cells (9 rows of z slices) around each boid's HOME cell,
+// fused with lead/attractor/bbox/steering terms and the Euler update.  One
+// binning serves many steps (lazy re-binning, fp_api.cu: grid_steps / settle):
+// the cell edge carries a skin, and a boid's home cell is the key its slot was
+// binned under.  The state stays in sorted order (pos.w carries the caller
+// index), so every global access is coalesced.  This file holds the binning
+// kernels and the simple walk forms (taps, cross-checks); the production walk
+// is fp_walk.cu.
 #include <stdlib.h>
 
 #include "fp_grid.cuh"

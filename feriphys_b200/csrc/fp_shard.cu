@@ -267,7 +267,7 @@ int shard_reduce_bounds(Shard *s, cudaStream_t st, float lo[3], float hi[3], flo
 constexpr int SB = 256;
 static inline unsigned nblk(size_t n) { return (unsigned)((n + SB - 1) / SB); }
 
-enum { REC_OWNED = 0u, REC_GHOST = 1u, REC_DEAD = 2u };
+enum { REC_OWNED = 0u, REC_DEAD = 2u };  // vel.w inside a binning: still here / migrated away or unused
 
 // owned boids of a slab-resident array -> their rows of a zeroed index-ordered flock
 __global__ void scatter_owned_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ vel,

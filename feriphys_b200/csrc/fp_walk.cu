@@ -77,7 +77,7 @@ struct Walk3Smem {
     alignas(8) uint64_t bar;
 };
 
-template <int TAP, int BLOCK, int TILE_CAP, int CAP, int PH>
+template <int TAP, int BLOCK, int TILE_CAP, int CAP>
 __global__ void __launch_bounds__(BLOCK, 768 / BLOCK)
 grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned *__restrict__ status,
                   TapOut tap) {
@@ -296,9 +296,9 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
                 }
                 if (!more) break;
                 const uint32_t i1 = min(i + (uint32_t)room, len);
-                // phase 1: exact distance gate.  PH candidates per batch, all tile loads issued
-                // ahead of the list stores; full batches carry no tail logic, and the (masked)
-                // tail may read up to PH-1 records past its range -- the tile is padded for that.
+                // phase 1, the pre-gate.  Four candidates per batch, all tile loads issued ahead of
+                // the list stores; full batches carry no tail logic, and the (masked) tail may
+                // read up to three records past its range -- the tile is padded for that.
                 uint32_t w = (uint32_t)cnt * BLOCK;  // list cursor, in entries
                 const uint32_t tag = (uint32_t)r << 12;
                 // Batches of four candidates at an even tile index: two neighbours load as one
@@ -359,10 +359,10 @@ grid_walk3_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned
     walk_finish<TAP>(P, s, pi4, vi4, self, acc, 0u, 0ull, io, status, tap);
 }
 
-template <int TAP, int BLOCK, int TILE_CAP, int CAP, int PH>
+template <int TAP, int BLOCK, int TILE_CAP, int CAP>
 static int launch3(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, unsigned *status,
                    const TapOut &tap_out) {
-    auto kern = grid_walk3_kernel<TAP, BLOCK, TILE_CAP, CAP, PH>;
+    auto kern = grid_walk3_kernel<TAP, BLOCK, TILE_CAP, CAP>;
     const int smem = (int)sizeof(Walk3Smem<BLOCK, TILE_CAP, CAP>);
     FP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<(io.last - io.first + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(P, g, io, status, tap_out);
@@ -373,19 +373,19 @@ static int launch3(cudaStream_t st, const DevParams &P, const GridDesc &g, const
 
 int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, int variant,
                       const WalkIO &io, unsigned *status, const TapOut &tap_out) {
-#define FP_W3(B, T, C, H)                                                          \
-    return tap == TAP_STEP ? launch3<TAP_STEP, B, T, C, H>(st, P, g, io, status, tap_out) \
-                           : launch3<TAP_ACCEL, B, T, C, H>(st, P, g, io, status, tap_out)
+#define FP_W3(B, T, C)                                                          \
+    return tap == TAP_STEP ? launch3<TAP_STEP, B, T, C>(st, P, g, io, status, tap_out) \
+                           : launch3<TAP_ACCEL, B, T, C>(st, P, g, io, status, tap_out)
     switch (variant) {
-        case 31: FP_W3(128, 1904, 64, 4);   // 43.6 KB: still 5 CTAs / SM, and the tile overflows ~never
-        case 38: FP_W3(128, 1792, 64, 4);   // 42.2 KB
-        case 32: FP_W3(128, 1792, 40, 4);   // 37 KB: 6 CTAs / SM
-        case 33: FP_W3(128, 1792, 56, 4);   // 41 KB: 5 CTAs / SM
-        case 34: FP_W3(128, 1792, 48, 4);   // 39 KB: 5 CTAs / SM
-        case 35: FP_W3(128, 1792, 80, 4);   // 47 KB: 4 CTAs / SM
-        case 36: FP_W3(128, 1536, 64, 4);   // 40 KB: 5 CTAs / SM
-        case 37: FP_W3(64, 1024, 64, 4);    // 23 KB: 9 CTAs / SM
-        default: FP_W3(128, 1904, 64, 4);   // one drain per boid almost always: lists average 17 entries
+        case 31: FP_W3(128, 1904, 64);   // 43.6 KB: still 5 CTAs / SM, and the tile overflows ~never
+        case 38: FP_W3(128, 1792, 64);   // 42.2 KB
+        case 32: FP_W3(128, 1792, 40);   // 37 KB: 6 CTAs / SM
+        case 33: FP_W3(128, 1792, 56);   // 41 KB: 5 CTAs / SM
+        case 34: FP_W3(128, 1792, 48);   // 39 KB: 5 CTAs / SM
+        case 35: FP_W3(128, 1792, 80);   // 47 KB: 4 CTAs / SM
+        case 36: FP_W3(128, 1536, 64);   // 40 KB: 5 CTAs / SM
+        case 37: FP_W3(64, 1024, 64);    // 23 KB: 9 CTAs / SM
+        default: FP_W3(128, 1904, 64);   // one drain per boid almost always: lists average 17 entries
     }
 #undef FP_W3
 }
