@@ -1,0 +1,61 @@
+"""CPU property test of the grid path's exactness argument, with the same
+float32 arithmetic as the kernels (fp_grid.cuh: cell_coord = floor(fl(fl(x - origin) * inv)),
+clamped): for a cell edge of reach * (1 + 1/512) + skin, sliced zspan times along z, and boids
+that have drifted by up to skin / 2 from where they were binned, EVERY pair closer than `reach`
+has home cells at most one apart in x and y and at most zspan slices apart in z -- so the walk
+over the 27 cells (9 rows of 2 * zspan + 1 slices) around the home cell sees every neighbour,
+including boids clamped into edge cells from outside the fitted domain."""
+import numpy as np
+import pytest
+from scipy.spatial import cKDTree
+
+f32 = np.float32
+
+
+def _coord(x, origin, inv, dim):
+    c = np.floor((x.astype(f32) - f32(origin)).astype(f32) * f32(inv)).astype(np.int64)
+    return np.clip(c, 0, dim - 1)
+
+
+@pytest.mark.parametrize("reach,skin,zspan,extent,offset", [
+    (16.0, 0.0, 1, 300.0, 0.0),
+    (16.0, 0.11, 4, 300.0, 0.0),
+    (16.0, 2.0, 4, 500.0, 1000.0),       # large coordinates: coarser float32 spacing
+    (5.0, 0.6, 2, 90.0, -45.0),
+    (30.0, 0.25, 4, 2048.0, 0.0),
+])
+def test_in_range_pairs_stay_within_the_home_neighbourhood(reach, skin, zspan, extent, offset):
+    rng = np.random.default_rng(int(reach * 1000 + skin * 100 + zspan))
+    n = 60000
+    binned = (rng.random((n, 3)) * extent + offset).astype(f32)
+    # the grid is fitted to the bulk only: a tenth of the boids sit outside and are clamped
+    lo = binned.min(axis=0) + f32(0.05 * extent)
+    hi = binned.max(axis=0) - f32(0.05 * extent)
+    cell = reach * (1.0 + 1.0 / 512.0) + skin
+    dims = [int(np.floor((float(hi[a]) - float(lo[a])) / cell)) + 1 for a in range(3)]
+    dimz = int(np.floor((float(hi[2]) - float(lo[2])) / (cell / zspan))) + 1
+    inv = f32(1.0) / f32(cell)
+    invz = f32(zspan / cell)
+    cx = _coord(binned[:, 0], lo[0], inv, dims[0])
+    cy = _coord(binned[:, 1], lo[1], inv, dims[1])
+    cz = _coord(binned[:, 2], lo[2], invz, dimz)
+    # drift: up to skin / 2 in a random direction (the device bound is on the Euclidean norm)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d *= (rng.random((n, 1)) ** (1 / 3)) * (skin / 2)
+    cur = (binned.astype(np.float64) + d).astype(f32)
+    # every pair within reach NOW (float64 distance, a hair generous)
+    pairs = cKDTree(cur.astype(np.float64)).query_pairs(reach * (1 + 1e-6), output_type="ndarray")
+    assert len(pairs) > 10000
+    i, j = pairs[:, 0], pairs[:, 1]
+    assert np.abs(cx[i] - cx[j]).max() <= 1
+    assert np.abs(cy[i] - cy[j]).max() <= 1
+    assert np.abs(cz[i] - cz[j]).max() <= zspan
+    # and the bound is not vacuous: with eight times the allowed drift some neighbour is missed
+    if skin >= 0.5:
+        far = (binned.astype(np.float64) + 8 * d).astype(f32)
+        pf = cKDTree(far.astype(np.float64)).query_pairs(reach * (1 - 1e-6), output_type="ndarray")
+        a, b = pf[:, 0], pf[:, 1]
+        worst = max(np.abs(cx[a] - cx[b]).max(), np.abs(cy[a] - cy[b]).max(),
+                    (np.abs(cz[a] - cz[b]).max() + zspan - 1) // zspan)
+        assert worst >= 2
