@@ -424,6 +424,7 @@ int grid_rebin(fp_flock *f) {
     f->bin_valid = true;
     f->plan_left = plan_steps(f, 0.0f, 0.0f);
     ++f->stat_rebins;
+    f->nl_fresh = true;
     return FP_OK;
 }
 
@@ -444,6 +445,55 @@ WalkIO walk_io(fp_flock *f, bool stepping) {
         io.ctl = w.ctl;
     }
     return io;
+}
+
+// ---- standing candidate lists (fp_walk_nl.cu): experimental, FP_WALK_VARIANT=41, single GPU ----
+constexpr uint32_t NL_VCAP = 96;  // C3 / C4 density: 34 candidates per boid on average, ~70 at most
+
+bool nl_wanted(const fp_flock *f) {
+    static const bool on = [] {
+        const char *e = getenv("FP_WALK_VARIANT");
+        return e && atoi(e) == 41;
+    }();
+    return on && !f->shard && !f->nl_off && f->grid.skin > 0.0f;  // (no skin = a binning per step: nothing to re-use)
+}
+
+void nl_free(fp_flock *f) {
+    dev_free(f->nl_entries);
+    dev_free(f->nl_count);
+    dev_free(f->nl_cta_tab);
+    dev_free(f->nl_flag);
+    f->nl_rows = 0;
+    f->nl_serial = ~0ull;
+}
+
+int nl_ensure(fp_flock *f) {
+    if (f->nl_entries && f->nl_rows >= f->n) return FP_OK;
+    nl_free(f);
+    int rc;
+    const size_t entries = nl_entries_elems(f->n, NL_VCAP);
+    if ((rc = dev_alloc(&f->nl_entries, entries)) || (rc = dev_alloc(&f->nl_count, (size_t)f->n)) ||
+        (rc = dev_alloc(&f->nl_cta_tab, nl_cta_tab_elems(f->n))) || (rc = dev_alloc(&f->nl_flag, 1)))
+        return rc;
+    FP_CUDA(cudaMemsetAsync(f->nl_entries, 0, entries * sizeof(uint16_t), f->stream));
+    FP_CUDA(cudaMemsetAsync(f->nl_flag, 0, sizeof(unsigned), f->stream));
+    f->nl_rows = f->n;
+    if (getenv("FP_NL_TRACE")) fprintf(stderr, "fp: candidate lists on (%u boids, %u entries each)\n", f->n, NL_VCAP);
+    return FP_OK;
+}
+
+NlIO nl_io(const fp_flock *f) {
+    NlIO nl{};
+    nl.entries = f->nl_entries;
+    nl.count = f->nl_count;
+    nl.cta_tab = f->nl_cta_tab;
+    nl.flag = f->nl_flag;
+    nl.vcap = NL_VCAP;
+    // every pair within reach while the binning stands was within reach + skin when it was made
+    const double R = (double)reach_of(f->cfg) + (double)f->grid.skin;
+    nl.m2_wide = nextafterf((float)(R * R * (1.0 + 1e-5)), INFINITY);
+    nl.ordinal = f->ordinal;
+    return nl;
 }
 
 // timing hook: record the next pooled event on the stream (no-op unless timing)
@@ -479,9 +529,20 @@ int grid_steps(fp_flock *f, uint32_t nsteps) {
         } else if ((rc = launch_skin_gate(f->stream, f->work.ctl, f->ordinal, 0, f->P.dt, f->skin_budget))) {
             return rc;
         }
+        if (nl_wanted(f) && f->nl_fresh && f->nl_serial != f->stat_rebins) {
+            // experimental: candidate lists that stand as long as this binning (made just now, or by
+            // a tap since the last step: either way the positions are still the binned ones)
+            if ((rc = nl_ensure(f)) || (rc = launch_nl_build(f->stream, f->grid, walk_io(f, true), nl_io(f))))
+                return rc;
+            f->nl_serial = f->stat_rebins;
+        }
         if ((rc = mark_event(f))) return rc;
-        if ((rc = launch_grid_walk(f->stream, f->P, f->grid, TAP_STEP, walk_io(f, true), f->d_status, TapOut{})))
-            return rc;
+        if (nl_wanted(f) && f->nl_serial == f->stat_rebins)
+            rc = launch_nl_walk(f->stream, f->P, walk_io(f, true), nl_io(f), f->d_status);
+        else
+            rc = launch_grid_walk(f->stream, f->P, f->grid, TAP_STEP, walk_io(f, true), f->d_status, TapOut{});
+        if (rc) return rc;
+        f->nl_fresh = false;
         f->cur ^= 1;
         f->work.soa_cur ^= 1;
         if ((rc = mark_event(f))) return rc;
@@ -520,6 +581,16 @@ int settle(fp_flock *f) {
         if (k == f->pending.size()) {
             set_error("internal: stale step not in the pending log");
             return FP_ERR_INVALID;
+        }
+        if (f->nl_flag) {  // was it a candidate-list overflow that voided the step?  Then no more lists
+            unsigned flag = 0;
+            FP_CUDA(cudaMemcpyAsync(&flag, f->nl_flag, sizeof(flag), cudaMemcpyDeviceToHost, f->stream));
+            FP_CUDA(cudaStreamSynchronize(f->stream));
+            if (flag) {
+                if (getenv("FP_NL_TRACE")) fprintf(stderr, "fp: candidate lists overflowed, off\n");
+                f->nl_off = true;
+                FP_CUDA(cudaMemsetAsync(f->nl_flag, 0, sizeof(flag), f->stream));
+            }
         }
         const fp_flock::Pending at = f->pending[k];
         const uint32_t redo = (uint32_t)(f->pending.size() - k);
@@ -717,6 +788,7 @@ int fp_flock_destroy(fp_flock *f) {
     dev_free(f->d_leads); dev_free(f->d_attr); dev_free(f->d_obs); dev_free(f->d_lead_table);
     dev_free(f->d_status); dev_free(f->d_census); dev_free(f->d_bounds);
     free_grid_work(f);
+    nl_free(f);
     if (f->d_stage) cudaFree(f->d_stage);
     if (f->h_ctl) cudaFreeHost(f->h_ctl);
     for (auto &ev : f->ev_pool) if (ev) cudaEventDestroy(ev);
@@ -737,6 +809,7 @@ int fp_flock_set_config(fp_flock *f, const fp_config *cfg) {
     derive_params(f->cfg, f->P);
     if (reach_of(f->cfg) != old_reach) f->grid_valid = false;
     f->bin_valid = false;  // dt and reach enter the skin accounting
+    f->nl_off = false;
     f->ap_choice = -1;     // a new reach changes which all-pairs kernel wins
     f->ap_probe = 0;
     return FP_OK;
@@ -1017,6 +1090,7 @@ int fp_flock_write_state(fp_flock *f, const float *state) {
     FP_CUDA(cudaStreamSynchronize(f->stream));
     f->permuted = false;
     f->bin_valid = false;
+    f->nl_off = false;
     if (!f->domain_user) f->grid_valid = false;
     return FP_OK;
 }
