@@ -447,15 +447,19 @@ WalkIO walk_io(fp_flock *f, bool stepping) {
     return io;
 }
 
-// ---- standing candidate lists (fp_walk_nl.cu): experimental, FP_WALK_VARIANT=41, single GPU ----
+// ---- standing candidate lists (fp_walk_nl.cu): experimental ----------------------------------
+// FP_WALK_VARIANT=41: single-GPU grid flocks (checked on a B200 against the production walk,
+// DESIGN.md 4.2); 42: sharded grid flocks as well (same kernels over the owned slots of a slab;
+// not yet run on hardware).
 constexpr uint32_t NL_VCAP = 96;  // C3 / C4 density: 34 candidates per boid on average, ~70 at most
 
 bool nl_wanted(const fp_flock *f) {
-    static const bool on = [] {
+    static const int variant = [] {
         const char *e = getenv("FP_WALK_VARIANT");
-        return e && atoi(e) == 41;
+        return e ? atoi(e) : 0;
     }();
-    return on && !f->shard && !f->nl_off && f->grid.skin > 0.0f;  // (no skin = a binning per step: nothing to re-use)
+    const bool on = f->shard ? variant == 42 : (variant == 41 || variant == 42);
+    return on && !f->nl_off && f->grid.skin > 0.0f;  // (no skin = a binning per step: nothing to re-use)
 }
 
 void nl_free(fp_flock *f) {
@@ -467,18 +471,38 @@ void nl_free(fp_flock *f) {
     f->nl_serial = ~0ull;
 }
 
-int nl_ensure(fp_flock *f) {
-    if (f->nl_entries && f->nl_rows >= f->n) return FP_OK;
+int nl_ensure(fp_flock *f, uint32_t rows) {
+    if (f->nl_entries && f->nl_rows >= rows) return FP_OK;
     nl_free(f);
+    // a slab's owned count changes from binning to binning: leave room so that it rarely re-allocates
+    const uint32_t cap = f->shard ? rows + rows / 8 + 4096 : rows;
     int rc;
-    const size_t entries = nl_entries_elems(f->n, NL_VCAP);
-    if ((rc = dev_alloc(&f->nl_entries, entries)) || (rc = dev_alloc(&f->nl_count, (size_t)f->n)) ||
-        (rc = dev_alloc(&f->nl_cta_tab, nl_cta_tab_elems(f->n))) || (rc = dev_alloc(&f->nl_flag, 1)))
+    const size_t entries = nl_entries_elems(cap, NL_VCAP);
+    if ((rc = dev_alloc(&f->nl_entries, entries)) || (rc = dev_alloc(&f->nl_count, (size_t)cap)) ||
+        (rc = dev_alloc(&f->nl_cta_tab, nl_cta_tab_elems(cap))) || (rc = dev_alloc(&f->nl_flag, 1)))
         return rc;
     FP_CUDA(cudaMemsetAsync(f->nl_entries, 0, entries * sizeof(uint16_t), f->stream));
     FP_CUDA(cudaMemsetAsync(f->nl_flag, 0, sizeof(unsigned), f->stream));
-    f->nl_rows = f->n;
-    if (getenv("FP_NL_TRACE")) fprintf(stderr, "fp: candidate lists on (%u boids, %u entries each)\n", f->n, NL_VCAP);
+    f->nl_rows = cap;
+    if (getenv("FP_NL_TRACE")) fprintf(stderr, "fp: candidate lists on (%u boids, %u entries each)\n", rows, NL_VCAP);
+    return FP_OK;
+}
+
+// Before a new build: how did the last one go?  CTAs without lists walk from global memory, which
+// is far slower than the production kernel; when more than 1 in 32 had none (and more than a
+// handful), the flock is too dense for lists of this size and the production walk takes over
+// (until a new state / config arrives).
+int nl_review(fp_flock *f) {
+    if (!f->nl_flag) return FP_OK;
+    unsigned none = 0;
+    FP_CUDA(cudaMemcpyAsync(&none, f->nl_flag, sizeof(none), cudaMemcpyDeviceToHost, f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));  // (a binning has just settled: the stream is all but idle)
+    FP_CUDA(cudaMemsetAsync(f->nl_flag, 0, sizeof(none), f->stream));
+    if (getenv("FP_NL_TRACE") && none) fprintf(stderr, "fp: %u CTAs without candidate lists in the last build\n", none);
+    if (none > 8 && (uint64_t)none * 32u > ((uint64_t)f->nl_built_rows + 127u) / 128u) {
+        if (getenv("FP_NL_TRACE")) fprintf(stderr, "fp: candidate lists off\n");
+        f->nl_off = true;
+    }
     return FP_OK;
 }
 
@@ -492,8 +516,29 @@ NlIO nl_io(const fp_flock *f) {
     // every pair within reach while the binning stands was within reach + skin when it was made
     const double R = (double)reach_of(f->cfg) + (double)f->grid.skin;
     nl.m2_wide = nextafterf((float)(R * R * (1.0 + 1e-5)), INFINITY);
-    nl.ordinal = f->ordinal;
     return nl;
+}
+
+// Called once per step, after the binning / gate and before the walk: builds the lists when the
+// flock has just been binned (by this step, or by a tap since the last step -- either way the
+// positions are still the binned ones) and the lists on hand describe an older binning.
+int nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) {
+    if (!nl_wanted(f) || !f->nl_fresh || f->nl_serial == f->stat_rebins) return FP_OK;
+    int rc = nl_review(f);  // (may turn the lists off)
+    if (rc || !nl_wanted(f)) return rc;
+    const uint32_t rows = io.last - io.first;
+    if ((rc = nl_ensure(f, rows)) || (rc = launch_nl_build(f->stream, g, io, nl_io(f)))) return rc;
+    f->nl_serial = f->stat_rebins;
+    f->nl_built_rows = rows;
+    return FP_OK;
+}
+
+// the step's walk: on the lists when they describe the standing binning, else the production kernel
+int nl_or_production_walk(fp_flock *f, const GridDesc &g, const WalkIO &io) {
+    f->nl_fresh = false;
+    if (nl_wanted(f) && f->nl_serial == f->stat_rebins)
+        return launch_nl_walk(f->stream, f->P, g, io, nl_io(f), f->d_status);
+    return launch_grid_walk(f->stream, f->P, g, TAP_STEP, io, f->d_status, TapOut{});
 }
 
 // timing hook: record the next pooled event on the stream (no-op unless timing)
@@ -529,20 +574,9 @@ int grid_steps(fp_flock *f, uint32_t nsteps) {
         } else if ((rc = launch_skin_gate(f->stream, f->work.ctl, f->ordinal, 0, f->P.dt, f->skin_budget))) {
             return rc;
         }
-        if (nl_wanted(f) && f->nl_fresh && f->nl_serial != f->stat_rebins) {
-            // experimental: candidate lists that stand as long as this binning (made just now, or by
-            // a tap since the last step: either way the positions are still the binned ones)
-            if ((rc = nl_ensure(f)) || (rc = launch_nl_build(f->stream, f->grid, walk_io(f, true), nl_io(f))))
-                return rc;
-            f->nl_serial = f->stat_rebins;
-        }
+        if ((rc = nl_prepare(f, f->grid, walk_io(f, true)))) return rc;  // (experimental; no-op by default)
         if ((rc = mark_event(f))) return rc;
-        if (nl_wanted(f) && f->nl_serial == f->stat_rebins)
-            rc = launch_nl_walk(f->stream, f->P, walk_io(f, true), nl_io(f), f->d_status);
-        else
-            rc = launch_grid_walk(f->stream, f->P, f->grid, TAP_STEP, walk_io(f, true), f->d_status, TapOut{});
-        if (rc) return rc;
-        f->nl_fresh = false;
+        if ((rc = nl_or_production_walk(f, f->grid, walk_io(f, true)))) return rc;
         f->cur ^= 1;
         f->work.soa_cur ^= 1;
         if ((rc = mark_event(f))) return rc;
@@ -581,16 +615,6 @@ int settle(fp_flock *f) {
         if (k == f->pending.size()) {
             set_error("internal: stale step not in the pending log");
             return FP_ERR_INVALID;
-        }
-        if (f->nl_flag) {  // was it a candidate-list overflow that voided the step?  Then no more lists
-            unsigned flag = 0;
-            FP_CUDA(cudaMemcpyAsync(&flag, f->nl_flag, sizeof(flag), cudaMemcpyDeviceToHost, f->stream));
-            FP_CUDA(cudaStreamSynchronize(f->stream));
-            if (flag) {
-                if (getenv("FP_NL_TRACE")) fprintf(stderr, "fp: candidate lists overflowed, off\n");
-                f->nl_off = true;
-                FP_CUDA(cudaMemsetAsync(f->nl_flag, 0, sizeof(flag), f->stream));
-            }
         }
         const fp_flock::Pending at = f->pending[k];
         const uint32_t redo = (uint32_t)(f->pending.size() - k);
@@ -633,6 +657,8 @@ int run_tap(fp_flock *f, int tap, const TapOut &out) {
 // entry points fp_shard.cu needs from this file
 namespace fp {
 int flock_fit_grid(fp_flock *f) { return fit_grid(f); }
+int flock_nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) { return nl_prepare(f, g, io); }
+int flock_step_walk(fp_flock *f, const GridDesc &g, const WalkIO &io) { return nl_or_production_walk(f, g, io); }
 void flock_select_leads(fp_flock *f) { select_leads(f); }
 int64_t flock_plan_steps(const fp_flock *f, float D, float first_delta) { return plan_steps(f, D, first_delta); }
 float flock_plan_delta(float v2max, float pmax, float dt) { return plan_delta(v2max, pmax, dt); }

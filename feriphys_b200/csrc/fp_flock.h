@@ -53,11 +53,12 @@ struct fp_flock {
     uint32_t timed_steps = 0;
     float skin_override = -1.0f;  // < 0: sized from the flock's speed at every fit
     float plan_scale = 1.0f;      // stretches the planned steps per binning (tests)
-    // standing candidate lists (fp_walk_nl.cu; experimental, FP_WALK_VARIANT=41)
+    // standing candidate lists (fp_walk_nl.cu; experimental, FP_WALK_VARIANT=41 / 42)
     uint16_t *nl_entries = nullptr, *nl_count = nullptr;
     uint32_t *nl_cta_tab = nullptr;
     unsigned *nl_flag = nullptr;
     uint32_t nl_rows = 0;        // boids the buffers are sized for
+    uint32_t nl_built_rows = 0;  // boids of the last build
     uint64_t nl_serial = ~0ull;  // stat_rebins of the binning the lists describe
     bool nl_fresh = false;       // the flock was binned and has not stepped since: lists may be built
     bool nl_off = false;         // a list overflowed: production walk until a new state / config arrives

@@ -165,18 +165,18 @@ int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, in
 struct NlIO {
     uint16_t *entries;   // [cta][vcap][128]: tile offsets (row << 12 | offset) of the candidates in reach + skin
     uint16_t *count;     // [slot - first]: entries of each boid
-    uint32_t *cta_tab;   // [cta][20]: the nine staged intervals of each CTA
-    unsigned *flag;      // set when a list or a tile overflowed: the lists are unusable
+    uint32_t *cta_tab;   // [cta][20]: the nine staged intervals of each CTA, [18] != 0: this CTA has no lists
+    unsigned *flag;      // CTAs the last build left without lists (tile or list overflow)
     uint32_t vcap;       // list capacity, a multiple of 4
     float m2_wide;       // build cut: (reach + skin)^2 (1 + 1e-5)
-    uint32_t ordinal;    // ordinal of the step the build belongs to (voided on overflow)
 };
 size_t nl_entries_elems(uint32_t rows, uint32_t vcap);
 size_t nl_cta_tab_elems(uint32_t rows);
 // after a binning, before its first walk
 int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl);
 // a step (TAP_STEP) on the standing lists; same result as launch_grid_walk
-int launch_nl_walk(cudaStream_t st, const DevParams &P, const WalkIO &io, const NlIO &nl, unsigned *status);
+int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, const NlIO &nl,
+                   unsigned *status);
 
 // Lazy re-binning control (fp_misc.cu).  Runs before each grid step: on a re-binning step it
 // resets the displacement bound, otherwise it adds the last walk's bound

@@ -927,6 +927,7 @@ static int slab_rebin(Shard *s, fp_flock *f) {
     f->steps_since_bin = 0;
     f->plan_left = flock_plan_steps(f, 0.0f, 0.0f);
     ++f->stat_rebins;
+    f->nl_fresh = true;
     s->global_valid = false;
     return FP_OK;
 }
@@ -1028,10 +1029,9 @@ static int slab_steps(Shard *s, fp_flock *f, uint32_t nsteps) {
                                           f->d_status))) {
             return rc;
         }
+        if ((rc = flock_nl_prepare(f, s->lgrid, slab_walk_io(s, f, true)))) return rc;  // (experimental; no-op by default)
         if ((rc = flock_mark(f))) return rc;
-        if ((rc = launch_grid_walk(f->stream, f->P, s->lgrid, TAP_STEP, slab_walk_io(s, f, true), f->d_status,
-                                   TapOut{})))
-            return rc;
+        if ((rc = flock_step_walk(f, s->lgrid, slab_walk_io(s, f, true)))) return rc;
         if ((rc = slab_post(s, f))) return rc;
         f->cur ^= 1;
         w.soa_cur ^= 1;

@@ -9,6 +9,9 @@ namespace fp {
 int flock_fit_grid(fp_flock *f);
 void flock_select_leads(fp_flock *f);
 int flock_mark(fp_flock *f);  // timing-hook event
+// experimental candidate lists (fp_walk_nl.cu): build after a binning if wanted; the step's walk
+int flock_nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io);
+int flock_step_walk(fp_flock *f, const GridDesc &g, const WalkIO &io);  // lists if on hand, else production
 // one all-pairs step launch with the staged / one-phase choice made by measurement
 int flock_allpairs_step(fp_flock *f, const float4 *pos_all, const float4 *vel_all, uint32_t n_all, uint32_t row0,
                         uint32_t nrows, float4 *pos_out, float4 *vel_out);

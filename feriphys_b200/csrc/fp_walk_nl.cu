@@ -25,10 +25,11 @@
 // and the result is bit-identical to the production kernel's (and to the oracle's on the
 // standing listing).
 //
-// Capacity.  A list holds NL_VCAP entries.  A boid with more, or a CTA whose tile does not fit,
-// raises `flag` and voids the step through the lazy re-binning's own mechanism (ctl->stale):
-// settle() sees the flag, turns the lists off for this grid fit and replays the step with the
-// production kernel.
+// Capacity.  A list holds nl.vcap entries.  A CTA in which some boid has more, or whose nine
+// intervals do not fit the tile, is marked in its layout record and walks the 27 cells from
+// global memory every step (the production kernel's own path for CTAs that overflow the tile):
+// slower, same result, no effect on any other CTA.  The build counts such CTAs; the host turns
+// the lists off when they stop being rare.
 #include "fp_walk_stage.cuh"
 
 namespace fp {
@@ -38,12 +39,11 @@ namespace {
 constexpr int NL_BLOCK = 128;   // threads (= boids) per CTA, as the production walk
 constexpr int NL_TILE = 1904;   // staged candidates per CTA, as the production walk
 constexpr int NL_CAP = 64;      // survivor list (shared memory), as the production walk
-constexpr int NL_CTA_WORDS = 20;  // cached tile layout per CTA: ub[9], ue[9], 2 spare
+constexpr int NL_CTA_WORDS = 20;  // cached tile layout per CTA: ub[9], ue[9], [18] = no lists, 1 spare
 
-// void the step and every later one (the protocol of skin_gate_kernel): the host replays
-__device__ __forceinline__ void nl_fail(const NlIO &nl, SkinCtl *ctl) {
-    atomicExch(nl.flag, 1u);
-    if (ctl && atomicExch(&ctl->stale, 1u) == 0u) ctl->first_stale = nl.ordinal;
+// this CTA gets no lists: it walks from global memory every step (counted once per CTA)
+__device__ __forceinline__ void nl_no_lists(const NlIO &nl, uint32_t *tab) {
+    if (atomicExch(tab + 18, 1u) == 0u) atomicAdd(nl.flag, 1u);
 }
 
 // Lays the nine CTA-wide intervals (ub, ue: multiples of 4, empty = 0, 0) out in the tile and
@@ -88,13 +88,18 @@ struct NlBuildSmem {
 
 __global__ void __launch_bounds__(NL_BLOCK)
 nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
-    if (io.ctl && io.ctl->stale) return;
+    // (No look at ctl->stale: the lists describe the binning, which stands whether or not the
+    // step they are built in turns out void.)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     NlBuildSmem &S = *reinterpret_cast<NlBuildSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
     const bool active = s < io.last;
-    if (tid == 0) mbar_init(&S.bar, 1);
+    uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
+    if (tid == 0) {
+        mbar_init(&S.bar, 1);
+        tab[18] = 0u;  // (ordered before any nl_no_lists of this CTA by the barriers below)
+    }
     if (tid < 9) {
         S.ub[tid] = 0xffffffffu;
         S.ue[tid] = 0u;
@@ -145,7 +150,6 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
         if (tid < 9) {
             S.ub[tid] = ub;
             S.ue[tid] = ue;
-            uint32_t *tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
             tab[tid] = ub;       // the layout every nl_walk_kernel launch of this binning re-uses
             tab[9 + tid] = ue;
         }
@@ -153,8 +157,8 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     }
     __syncthreads();
     const uint32_t total = S.toff[9];
-    if (total > (uint32_t)NL_TILE) {  // dense cluster: the tile does not fit -- no lists for this flock
-        if (tid == 0) nl_fail(nl, io.ctl);
+    if (total > (uint32_t)NL_TILE) {  // dense cluster: the tile does not fit -- no lists for this CTA
+        if (tid == 0) nl_no_lists(nl, tab);
         return;
     }
 #pragma unroll
@@ -209,7 +213,7 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
         }
     }
     if (active) nl.count[s - io.first] = (uint16_t)min(w, vcap);
-    if (__any_sync(0xffffffffu, w > vcap) && (tid & 31) == 0) nl_fail(nl, io.ctl);
+    if (__any_sync(0xffffffffu, w > vcap) && (tid & 31) == 0) nl_no_lists(nl, tab);
 }
 
 struct NlWalkSmem {
@@ -220,7 +224,7 @@ struct NlWalkSmem {
 };
 
 __global__ void __launch_bounds__(NL_BLOCK, 5)  // shared memory (39 KB) allows five CTAs per SM: 102 registers
-nl_walk_kernel(const DevParams P, const WalkIO io, const NlIO nl, unsigned *__restrict__ status) {
+nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO nl, unsigned *__restrict__ status) {
     if (io.ctl && io.ctl->stale) return;  // lazy re-binning: this step is void
     const float4 *__restrict__ vel_s = io.vel_s;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -251,18 +255,46 @@ nl_walk_kernel(const DevParams P, const WalkIO io, const NlIO nl, unsigned *__re
         work = !ghost && !P.steering_overrides;
     }
     if (!work) n_c = 0;
+    const uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
+    V3 acc = v3zero();
+    if (__ldg(tab + 18)) {
+        // a CTA without lists (tile or list overflow at build time): the one-phase walk of the 27
+        // home cells from global memory, as the production kernel does for its overflowing CTAs
+        if (work) {
+            int cx, cy, cz;
+            home_cell(g, __ldg(io.home + (s - io.first)), cx, cy, cz);
+            const int z0 = max(cz - g.zspan, 0), z1 = min(cz + g.zspan, g.dim[2] - 1);
+            for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x) {
+                for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+                    const uint32_t rowbase = row_base(g, x, y);
+                    const uint32_t b = __ldg(io.cell_start + rowbase + z0);
+                    const uint32_t e = __ldg(io.cell_start + rowbase + z1 + 1);
+                    for (uint32_t j = b; j < e; ++j) {
+                        if (j == s) continue;
+                        const float4 pj = __ldg(io.pos_s + j);
+                        V3 d;
+                        const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
+                        if (m2 >= P.m2_cut) continue;
+                        const float4 vj = __ldg(vel_s + j);
+                        V3 contrib;
+                        if (pair_flock(P, self, d, m2, v3(vj.x, vj.y, vj.z), contrib)) acc = vadd(acc, contrib);
+                    }
+                }
+            }
+        }
+        if (active) walk_finish<TAP_STEP>(P, s, pi4, vi4, self, acc, 0u, 0ull, io, status, TapOut{});
+        return;
+    }
     __syncthreads();  // the barrier is initialised
     if (tid < 32) {
-        const uint32_t *tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
         const uint32_t ub = tid < 9 ? __ldg(tab + tid) : 0u, ue = tid < 9 ? __ldg(tab + 9 + tid) : 0u;
         nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], NL_TILE);
     }
     __syncthreads();
     const uint32_t t_self = work ? s - S.tslot[4] : 0xffffu;
     const uint32_t nmax = __reduce_max_sync(0xffffffffu, n_c);
-    if (S.toff[9] > 0 && S.toff[9] <= (uint32_t)NL_TILE) mbar_wait(&S.bar, 0);
+    if (S.toff[9] > 0) mbar_wait(&S.bar, 0);  // (a layout with lists always fits the tile)
 
-    V3 acc = v3zero();
     uint16_t *const lst = &S.list[0][tid];  // entry k at lst[k * BLOCK]
     int cnt = 0;
     uint32_t base = 0;  // warp-uniform progress through the cached lists, a multiple of 4
@@ -337,11 +369,12 @@ int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const 
     return FP_OK;
 }
 
-int launch_nl_walk(cudaStream_t st, const DevParams &P, const WalkIO &io, const NlIO &nl, unsigned *status) {
+int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, const NlIO &nl,
+                   unsigned *status) {
     if (io.last <= io.first) return FP_OK;
     const int smem = (int)sizeof(NlWalkSmem);
     FP_CUDA(cudaFuncSetAttribute(nl_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    nl_walk_kernel<<<(io.last - io.first + NL_BLOCK - 1) / NL_BLOCK, NL_BLOCK, smem, st>>>(P, io, nl, status);
+    nl_walk_kernel<<<(io.last - io.first + NL_BLOCK - 1) / NL_BLOCK, NL_BLOCK, smem, st>>>(P, g, io, nl, status);
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;

@@ -59,3 +59,41 @@ def test_in_range_pairs_stay_within_the_home_neighbourhood(reach, skin, zspan, e
         worst = max(np.abs(cx[a] - cx[b]).max(), np.abs(cy[a] - cy[b]).max(),
                     (np.abs(cz[a] - cz[b]).max() + zspan - 1) // zspan)
         assert worst >= 2
+
+
+@pytest.mark.parametrize("reach,skin,extent,offset", [
+    (16.0, 0.11, 300.0, 0.0),
+    (16.0, 2.0, 500.0, 1000.0),
+    (5.0, 0.6, 90.0, -45.0),
+])
+def test_candidate_list_cut_keeps_every_pair_that_can_come_into_reach(reach, skin, extent, offset):
+    """The standing candidate lists (fp_walk_nl.cu) keep, at binning time, the pairs
+    whose FUSED float32 squared distance is below m2_wide = (reach + skin)^2 (1 + 1e-5).  While
+    every boid stays within skin / 2 of its binned position, every pair the step's pre-gate can
+    keep -- fused float32 squared distance below m2_cut (1 + 1e-6) -- must be among them."""
+    rng = np.random.default_rng(int(reach * 1000 + skin * 100))
+    n = 60000
+    binned = (rng.random((n, 3)) * extent + offset).astype(f32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d *= (skin / 2) * np.where(rng.random((n, 1)) < 0.5, 1.0, rng.random((n, 1)))  # half of them at the limit
+    cur = (binned.astype(np.float64) + d).astype(f32)
+    R = float(f32(reach)) + float(f32(skin))
+    m2_wide = np.nextafter(f32(R * R * (1.0 + 1e-5)), f32(np.inf))
+    m2_cut_hi = f32(float(f32(reach)) ** 2 * (1.0 + 2e-6))    # at least the kernels' m2_cut (1 + 1e-6)
+
+    def fused_m2(p, i, j):                                   # fma(dz, dz, fma(dy, dy, dx * dx)) in float32
+        dd = (p[j] - p[i]).astype(np.float64)                # the float32 differences, exactly
+        m = f32(dd[:, 0] * dd[:, 0])
+        m = (dd[:, 1] * dd[:, 1] + m.astype(np.float64)).astype(f32)
+        return (dd[:, 2] * dd[:, 2] + m.astype(np.float64)).astype(f32)
+
+    pairs = cKDTree(cur.astype(np.float64)).query_pairs(reach * (1 + 1e-4), output_type="ndarray")
+    i, j = pairs[:, 0], pairs[:, 1]
+    now = fused_m2(cur, i, j)
+    kept_now = now < m2_cut_hi
+    assert kept_now.sum() > 10000
+    then = fused_m2(binned, i[kept_now], j[kept_now])
+    assert (then < m2_wide).all()
+    # not vacuous: the closest call is within a few percent of the cut
+    assert float(then.max()) > 0.9 * float(m2_wide)

@@ -44,8 +44,22 @@ def main():
     sim.step_many(3)
     sim.sync()
     t0 = time.perf_counter()
-    sim.step_many(steps)
-    sim.sync()
+    chunk = int(os.environ.get("NL_CHUNK", "0"))     # diagnostic: sync every `chunk` steps, report progress
+    if chunk:
+        done = 0
+        while done < steps:
+            k = min(chunk, steps - done)
+            try:
+                sim.step_many(k)
+                sim.sync()
+            except Exception as e:
+                print(f"failed within steps {done + 1}..{done + k} (after the 3 warm-up steps): {e}", file=sys.stderr)
+                raise
+            done += k
+            print("progress", done, "rebin_info", sim.rebin_info(), "grid", sim.grid_info(), file=sys.stderr)
+    else:
+        sim.step_many(steps)
+        sim.sync()
     ms = 1e3 * (time.perf_counter() - t0) / steps
     out = sim.read_state()
     skin, nsteps, rebins, replayed = sim.rebin_info()
