@@ -449,16 +449,22 @@ WalkIO walk_io(fp_flock *f, bool stepping) {
 
 // ---- standing candidate lists (fp_walk_nl.cu): experimental ----------------------------------
 // FP_WALK_VARIANT=41: single-GPU grid flocks (checked on a B200 against the production walk,
-// DESIGN.md 4.2); 42: sharded grid flocks as well (same kernels over the owned slots of a slab;
-// not yet run on hardware).
+// DESIGN.md 4.2); 42: sharded grid flocks as well (same kernels over the owned slots of a slab);
+// 43: as 41 with the build's stores staged through shared memory.  42 and 43 have not run on
+// hardware yet.
 constexpr uint32_t NL_VCAP = 96;  // C3 / C4 density: 34 candidates per boid on average, ~70 at most
 
-bool nl_wanted(const fp_flock *f) {
+int nl_variant() {
     static const int variant = [] {
         const char *e = getenv("FP_WALK_VARIANT");
         return e ? atoi(e) : 0;
     }();
-    const bool on = f->shard ? variant == 42 : (variant == 41 || variant == 42);
+    return variant;
+}
+
+bool nl_wanted(const fp_flock *f) {
+    const int variant = nl_variant();
+    const bool on = f->shard ? variant == 42 : (variant >= 41 && variant <= 43);
     return on && !f->nl_off && f->grid.skin > 0.0f;  // (no skin = a binning per step: nothing to re-use)
 }
 
@@ -527,7 +533,7 @@ int nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) {
     int rc = nl_review(f);  // (may turn the lists off)
     if (rc || !nl_wanted(f)) return rc;
     const uint32_t rows = io.last - io.first;
-    if ((rc = nl_ensure(f, rows)) || (rc = launch_nl_build(f->stream, g, io, nl_io(f)))) return rc;
+    if ((rc = nl_ensure(f, rows)) || (rc = launch_nl_build(f->stream, g, io, nl_io(f), nl_variant() == 43))) return rc;
     f->nl_serial = f->stat_rebins;
     f->nl_built_rows = rows;
     return FP_OK;

@@ -173,7 +173,8 @@ struct NlIO {
 size_t nl_entries_elems(uint32_t rows, uint32_t vcap);
 size_t nl_cta_tab_elems(uint32_t rows);
 // after a binning, before its first walk
-int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl);
+// (staged: entries collected in shared memory and written as whole rows -- variant 43, untested)
+int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, bool staged = false);
 // a step (TAP_STEP) on the standing lists; same result as launch_grid_walk
 int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, const NlIO &nl,
                    unsigned *status);

@@ -85,7 +85,14 @@ struct NlBuildSmem {
     uint32_t toff[10], tslot[9];
     alignas(8) uint64_t bar;
 };
+constexpr int NL_STAGE_ROWS = 96;  // STAGED: rows of the shared-memory staging block (>= vcap)
 
+// STAGED = false: every entry goes straight to global memory -- a warp's 32 lanes are at 32
+// different list positions, so each 2-byte store touches its own sector (the form checked on
+// hardware, FP_WALK_VARIANT=41: a build costs 4.9 ms at C4).  STAGED = true (variant 43, not yet
+// run on hardware): entries are collected in shared memory, [entry][thread], and the CTA's
+// block is written row by row, 256 contiguous bytes per row.
+template <bool STAGED>
 __global__ void __launch_bounds__(NL_BLOCK)
 nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     // (No look at ctl->stale: the lists describe the binning, which stands whether or not the
@@ -170,7 +177,8 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     const uint32_t t_self = work ? s - S.tslot[4] : 0xffffu;  // tile offset of the boid itself (row 4)
     if (total > 0) mbar_wait(&S.bar, 0);
     uint16_t *const out = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + tid;  // entry k at out[k * BLOCK]
-    const uint32_t vcap = nl.vcap;
+    uint16_t *const stg = reinterpret_cast<uint16_t *>(smem_raw + sizeof(NlBuildSmem)) + tid;  // STAGED: same layout
+    const uint32_t vcap = STAGED ? min(nl.vcap, (uint32_t)NL_STAGE_ROWS) : nl.vcap;
     uint32_t w = 0;  // entries found
     const float2 nsx = make_float2(-pi4.x, -pi4.x), nsy = make_float2(-pi4.y, -pi4.y),
                  nsz = make_float2(-pi4.z, -pi4.z);
@@ -197,7 +205,7 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if ((live >> u & 1u) && !(mm[u] >= nl.m2_wide) && T + u != t_self) {  // NaN never drops
-                    if (w < vcap) out[(size_t)w * NL_BLOCK] = (uint16_t)(tag | (T + u));
+                    if (w < vcap) (STAGED ? stg : out)[(size_t)w * NL_BLOCK] = (uint16_t)(tag | (T + u));
                     ++w;
                 }
         };
@@ -214,6 +222,18 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     }
     if (active) nl.count[s - io.first] = (uint16_t)min(w, vcap);
     if (__any_sync(0xffffffffu, w > vcap) && (tid & 31) == 0) nl_no_lists(nl, tab);
+    if (STAGED) {
+        // rows 0 .. (longest list of the CTA) of the staging block, as they are: a thread's entries
+        // past its own count are whatever the shared memory held, and are never read as entries
+        __shared__ uint32_t wmax;  // longest list of the CTA
+        if (tid == 0) wmax = 0u;
+        __syncthreads();
+        const uint32_t wm = __reduce_max_sync(0xffffffffu, min(w, vcap));
+        if ((tid & 31) == 0) atomicMax(&wmax, wm);
+        __syncthreads();
+        const uint32_t rows = wmax;
+        for (uint32_t k = 0; k < rows; ++k) out[(size_t)k * NL_BLOCK] = stg[(size_t)k * NL_BLOCK];
+    }
 }
 
 struct NlWalkSmem {
@@ -359,11 +379,18 @@ size_t nl_cta_tab_elems(uint32_t rows) {
     return (((size_t)rows + NL_BLOCK - 1) / NL_BLOCK) * NL_CTA_WORDS;
 }
 
-int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl) {
+int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, bool staged) {
     if (io.last <= io.first) return FP_OK;
-    const int smem = (int)sizeof(NlBuildSmem);
-    FP_CUDA(cudaFuncSetAttribute(nl_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    nl_build_kernel<<<(io.last - io.first + NL_BLOCK - 1) / NL_BLOCK, NL_BLOCK, smem, st>>>(g, io, nl);
+    const uint32_t ctas = (io.last - io.first + NL_BLOCK - 1) / NL_BLOCK;
+    if (staged) {
+        const int smem = (int)(sizeof(NlBuildSmem) + sizeof(uint16_t) * NL_STAGE_ROWS * NL_BLOCK);
+        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        nl_build_kernel<true><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+    } else {
+        const int smem = (int)sizeof(NlBuildSmem);
+        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        nl_build_kernel<false><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+    }
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;
