@@ -450,8 +450,8 @@ WalkIO walk_io(fp_flock *f, bool stepping) {
 // ---- standing candidate lists (fp_walk_nl.cu): experimental ----------------------------------
 // FP_WALK_VARIANT=41: single-GPU grid flocks (checked on a B200 against the production walk,
 // DESIGN.md 4.2); 42: sharded grid flocks as well (same kernels over the owned slots of a slab);
-// 43: as 41 with the build's stores staged through shared memory.  42 and 43 have not run on
-// hardware yet.
+// 43: as 41 with the build's stores staged through shared memory; 44: as 41 with 48-entry survivor
+// lists and six CTAs per SM.  42, 43 and 44 have not run on hardware yet.
 constexpr uint32_t NL_VCAP = 96;  // C3 / C4 density: 34 candidates per boid on average, ~70 at most
 
 int nl_variant() {
@@ -464,7 +464,7 @@ int nl_variant() {
 
 bool nl_wanted(const fp_flock *f) {
     const int variant = nl_variant();
-    const bool on = f->shard ? variant == 42 : (variant >= 41 && variant <= 43);
+    const bool on = f->shard ? variant == 42 : (variant >= 41 && variant <= 44);
     return on && !f->nl_off && f->grid.skin > 0.0f;  // (no skin = a binning per step: nothing to re-use)
 }
 
@@ -543,7 +543,7 @@ int nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) {
 int nl_or_production_walk(fp_flock *f, const GridDesc &g, const WalkIO &io) {
     f->nl_fresh = false;
     if (nl_wanted(f) && f->nl_serial == f->stat_rebins)
-        return launch_nl_walk(f->stream, f->P, g, io, nl_io(f), f->d_status);
+        return launch_nl_walk(f->stream, f->P, g, io, nl_io(f), f->d_status, nl_variant() == 44);
     return launch_grid_walk(f->stream, f->P, g, TAP_STEP, io, f->d_status, TapOut{});
 }
 

@@ -176,8 +176,9 @@ size_t nl_cta_tab_elems(uint32_t rows);
 // (staged: entries collected in shared memory and written as whole rows -- variant 43, untested)
 int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, bool staged = false);
 // a step (TAP_STEP) on the standing lists; same result as launch_grid_walk
+// (six_ctas: 48-entry survivor lists, six CTAs per SM -- variant 44, untested)
 int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, const NlIO &nl,
-                   unsigned *status);
+                   unsigned *status, bool six_ctas = false);
 
 // Lazy re-binning control (fp_misc.cu).  Runs before each grid step: on a re-binning step it
 // resets the displacement bound, otherwise it adds the last walk's bound

@@ -236,19 +236,25 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     }
 }
 
+template <int CAP>
 struct NlWalkSmem {
     alignas(16) float tx[NL_TILE + 8], ty[NL_TILE + 8], tz[NL_TILE + 8];
-    uint16_t list[NL_CAP][NL_BLOCK];  // per-thread survivor lists: tile offsets
+    uint16_t list[CAP][NL_BLOCK];  // per-thread survivor lists: tile offsets
     uint32_t toff[10], tslot[9];
     alignas(8) uint64_t bar;
 };
 
-__global__ void __launch_bounds__(NL_BLOCK, 5)  // shared memory (39 KB) allows five CTAs per SM: 102 registers
+// <CAP, CTAS>: survivor-list capacity and the CTAs per SM the registers are budgeted for.
+// <64, 5> is the form checked on hardware (39 KB of shared memory: five CTAs per SM, 102
+// registers).  <48, 6> (variant 44, not yet run): 35 KB, six CTAs per SM at 80 registers -- with
+// ~17 survivors per boid a 48-entry list still drains once per boid almost always.
+template <int CAP, int CTAS>
+__global__ void __launch_bounds__(NL_BLOCK, CTAS)
 nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO nl, unsigned *__restrict__ status) {
     if (io.ctl && io.ctl->stale) return;  // lazy re-binning: this step is void
     const float4 *__restrict__ vel_s = io.vel_s;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    NlWalkSmem &S = *reinterpret_cast<NlWalkSmem *>(smem_raw);
+    NlWalkSmem<CAP> &S = *reinterpret_cast<NlWalkSmem<CAP> *>(smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
     const bool active = s < io.last;
@@ -321,12 +327,12 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     const float kh = P.fov_kh, kl = P.fov_kl;
 #pragma unroll 1
     for (;;) {
-        int room = NL_CAP - (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);
+        int room = CAP - (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);
         const bool more = base < nmax;
-        if (room < 4 || (!more && room < NL_CAP)) {
+        if (room < 4 || (!more && room < CAP)) {
             drain_list<NL_BLOCK>(P, self, lst, cnt, S.tx, S.ty, S.tz, S.tslot, t_self, vel_s, acc);
             cnt = 0;
-            room = NL_CAP;
+            room = CAP;
         }
         if (!more) break;
         const uint32_t end = min(base + ((uint32_t)room & ~3u), (nmax + 3u) & ~3u);
@@ -396,12 +402,22 @@ int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const 
     return FP_OK;
 }
 
+template <int CAP, int CTAS>
+static int launch_nl_walk_as(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io,
+                             const NlIO &nl, unsigned *status) {
+    const int smem = (int)sizeof(NlWalkSmem<CAP>);
+    auto kern = nl_walk_kernel<CAP, CTAS>;
+    FP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<(io.last - io.first + NL_BLOCK - 1) / NL_BLOCK, NL_BLOCK, smem, st>>>(P, g, io, nl, status);
+    return FP_OK;
+}
+
 int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, const NlIO &nl,
-                   unsigned *status) {
+                   unsigned *status, bool six_ctas) {
     if (io.last <= io.first) return FP_OK;
-    const int smem = (int)sizeof(NlWalkSmem);
-    FP_CUDA(cudaFuncSetAttribute(nl_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    nl_walk_kernel<<<(io.last - io.first + NL_BLOCK - 1) / NL_BLOCK, NL_BLOCK, smem, st>>>(P, g, io, nl, status);
+    const int rc = six_ctas ? launch_nl_walk_as<48, 6>(st, P, g, io, nl, status)
+                            : launch_nl_walk_as<NL_CAP, 5>(st, P, g, io, nl, status);
+    if (rc) return rc;
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;
