@@ -451,8 +451,19 @@ WalkIO walk_io(fp_flock *f, bool stepping) {
 // FP_WALK_VARIANT=41: single-GPU grid flocks (checked on a B200 against the production walk,
 // DESIGN.md 4.2); 42: sharded grid flocks as well (same kernels over the owned slots of a slab);
 // 43: as 41 with the build's stores staged through shared memory; 44: as 41 with 48-entry survivor
-// lists and six CTAs per SM.  42, 43 and 44 have not run on hardware yet.
+// lists and six CTAs per SM; 45: as 43 with a CTA's boids handed to its threads in order of list
+// length.  42 .. 45 have not run on hardware yet.
 constexpr uint32_t NL_VCAP = 96;  // C3 / C4 density: 34 candidates per boid on average, ~70 at most
+
+int nl_variant();
+int nl_form() {  // which form of the kernels the variant asks for (build and walk alike)
+    switch (nl_variant()) {
+        case 43: return NL_FORM_STAGED;
+        case 44: return NL_FORM_SIX_CTAS;
+        case 45: return NL_FORM_SORTED;
+        default: return NL_FORM_PLAIN;
+    }
+}
 
 int nl_variant() {
     static const int variant = [] {
@@ -464,7 +475,7 @@ int nl_variant() {
 
 bool nl_wanted(const fp_flock *f) {
     const int variant = nl_variant();
-    const bool on = f->shard ? variant == 42 : (variant >= 41 && variant <= 44);
+    const bool on = f->shard ? variant == 42 : (variant >= 41 && variant <= 45);
     return on && !f->nl_off && f->grid.skin > 0.0f;  // (no skin = a binning per step: nothing to re-use)
 }
 
@@ -484,7 +495,7 @@ int nl_ensure(fp_flock *f, uint32_t rows) {
     const uint32_t cap = f->shard ? rows + rows / 8 + 4096 : rows;
     int rc;
     const size_t entries = nl_entries_elems(cap, NL_VCAP);
-    if ((rc = dev_alloc(&f->nl_entries, entries)) || (rc = dev_alloc(&f->nl_count, (size_t)cap)) ||
+    if ((rc = dev_alloc(&f->nl_entries, entries)) || (rc = dev_alloc(&f->nl_count, (size_t)cap + 128)) ||
         (rc = dev_alloc(&f->nl_cta_tab, nl_cta_tab_elems(cap))) || (rc = dev_alloc(&f->nl_flag, 1)))
         return rc;
     FP_CUDA(cudaMemsetAsync(f->nl_entries, 0, entries * sizeof(uint16_t), f->stream));
@@ -533,7 +544,7 @@ int nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) {
     int rc = nl_review(f);  // (may turn the lists off)
     if (rc || !nl_wanted(f)) return rc;
     const uint32_t rows = io.last - io.first;
-    if ((rc = nl_ensure(f, rows)) || (rc = launch_nl_build(f->stream, g, io, nl_io(f), nl_variant() == 43))) return rc;
+    if ((rc = nl_ensure(f, rows)) || (rc = launch_nl_build(f->stream, g, io, nl_io(f), nl_form()))) return rc;
     f->nl_serial = f->stat_rebins;
     f->nl_built_rows = rows;
     return FP_OK;
@@ -543,7 +554,7 @@ int nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) {
 int nl_or_production_walk(fp_flock *f, const GridDesc &g, const WalkIO &io) {
     f->nl_fresh = false;
     if (nl_wanted(f) && f->nl_serial == f->stat_rebins)
-        return launch_nl_walk(f->stream, f->P, g, io, nl_io(f), f->d_status, nl_variant() == 44);
+        return launch_nl_walk(f->stream, f->P, g, io, nl_io(f), f->d_status, nl_form());
     return launch_grid_walk(f->stream, f->P, g, TAP_STEP, io, f->d_status, TapOut{});
 }
 

@@ -164,7 +164,7 @@ int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, in
 // distance pre-gate of the walk done once per binning instead of once per step.
 struct NlIO {
     uint16_t *entries;   // [cta][vcap][128]: tile offsets (row << 12 | offset) of the candidates in reach + skin
-    uint16_t *count;     // [slot - first]: entries of each boid
+    uint16_t *count;     // [slot - first]: entries of each boid (NL_FORM_SORTED: [cta * 128 + thread], boid << 8 | entries)
     uint32_t *cta_tab;   // [cta][20]: the nine staged intervals of each CTA, [18] != 0: this CTA has no lists
     unsigned *flag;      // CTAs the last build left without lists (tile or list overflow)
     uint32_t vcap;       // list capacity, a multiple of 4
@@ -173,12 +173,15 @@ struct NlIO {
 size_t nl_entries_elems(uint32_t rows, uint32_t vcap);
 size_t nl_cta_tab_elems(uint32_t rows);
 // after a binning, before its first walk
-// (staged: entries collected in shared memory and written as whole rows -- variant 43, untested)
-int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, bool staged = false);
+// Forms of the two kernels.  PLAIN is the one checked on hardware (FP_WALK_VARIANT=41); the others
+// are written but have not run yet: STAGED (43) collects the build's entries in shared memory and
+// writes whole rows; SIX_CTAS (44) walks with 48-entry survivor lists at six CTAs per SM; SORTED (45)
+// hands a CTA's boids to its threads in order of list length (build and walk must agree on it).
+enum { NL_FORM_PLAIN = 0, NL_FORM_STAGED = 1, NL_FORM_SIX_CTAS = 2, NL_FORM_SORTED = 3 };
+int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, int form = NL_FORM_PLAIN);
 // a step (TAP_STEP) on the standing lists; same result as launch_grid_walk
-// (six_ctas: 48-entry survivor lists, six CTAs per SM -- variant 44, untested)
 int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, const NlIO &nl,
-                   unsigned *status, bool six_ctas = false);
+                   unsigned *status, int form = NL_FORM_PLAIN);
 
 // Lazy re-binning control (fp_misc.cu).  Runs before each grid step: on a re-binning step it
 // resets the displacement bound, otherwise it adds the last walk's bound

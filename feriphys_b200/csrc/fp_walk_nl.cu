@@ -92,7 +92,14 @@ constexpr int NL_STAGE_ROWS = 96;  // STAGED: rows of the shared-memory staging 
 // hardware, FP_WALK_VARIANT=41: a build costs 4.9 ms at C4).  STAGED = true (variant 43, not yet
 // run on hardware): entries are collected in shared memory, [entry][thread], and the CTA's
 // block is written row by row, 256 contiguous bytes per row.
-template <bool STAGED>
+// SORTED (needs STAGED; variant 45, not yet run on hardware): the CTA's 128 boids are handed to its
+// threads in descending order of list length, so that the lanes of a warp walk lists of similar
+// length (candidate counts are Poisson, 35 +- 6: unsorted, a warp runs as long as its longest
+// list, ~46 entries).  Lane l of the CTA then holds boid (count[cta * 128 + l] >> 8) of the
+// CTA's slot window, with its list in column l; the count stays in the low byte.  Any
+// assignment of boids to threads gives the same result: each boid still sums its own
+// contributions in slot order.
+template <bool STAGED, bool SORTED>
 __global__ void __launch_bounds__(NL_BLOCK)
 nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     // (No look at ctl->stale: the lists describe the binning, which stands whether or not the
@@ -220,9 +227,34 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
             if (T < B) gate4(T, (1u << (B - T)) - 1u);
         }
     }
-    if (active) nl.count[s - io.first] = (uint16_t)min(w, vcap);
+    if (!SORTED && active) nl.count[s - io.first] = (uint16_t)min(w, vcap);
     if (__any_sync(0xffffffffu, w > vcap) && (tid & 31) == 0) nl_no_lists(nl, tab);
-    if (STAGED) {
+    if (STAGED && SORTED) {
+        static_assert(!SORTED || STAGED, "the sorted layout is written from the staging block");
+        __shared__ uint32_t hist[NL_STAGE_ROWS + 1];  // threads per list length, then running ranks
+        __shared__ uint32_t wmax_s;
+        const uint32_t c = min(w, vcap);
+        if (tid <= (uint32_t)NL_STAGE_ROWS) hist[tid] = 0u;
+        __syncthreads();
+        atomicAdd(&hist[c], 1u);
+        __syncthreads();
+        if (tid == 0) {  // first rank of each length, longest lists first
+            uint32_t run = 0, longest = 0;
+            for (int len = NL_STAGE_ROWS; len >= 0; --len) {
+                const uint32_t t = hist[len];
+                if (t && !longest) longest = (uint32_t)len;
+                hist[len] = run;
+                run += t;
+            }
+            wmax_s = longest;
+        }
+        __syncthreads();
+        const uint32_t rank = atomicAdd(&hist[c], 1u);  // (order within one length: whoever comes first)
+        nl.count[(size_t)blockIdx.x * NL_BLOCK + rank] = (uint16_t)(c | (tid << 8));
+        uint16_t *const col = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + rank;
+        const uint32_t rows = wmax_s;
+        for (uint32_t k = 0; k < rows; ++k) col[(size_t)k * NL_BLOCK] = stg[(size_t)k * NL_BLOCK];
+    } else if (STAGED) {
         // rows 0 .. (longest list of the CTA) of the staging block, as they are: a thread's entries
         // past its own count are whatever the shared memory held, and are never read as entries
         __shared__ uint32_t wmax;  // longest list of the CTA
@@ -248,7 +280,7 @@ struct NlWalkSmem {
 // <64, 5> is the form checked on hardware (39 KB of shared memory: five CTAs per SM, 102
 // registers).  <48, 6> (variant 44, not yet run): 35 KB, six CTAs per SM at 80 registers -- with
 // ~17 survivors per boid a 48-entry list still drains once per boid almost always.
-template <int CAP, int CTAS>
+template <int CAP, int CTAS, bool SORTED>
 __global__ void __launch_bounds__(NL_BLOCK, CTAS)
 nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO nl, unsigned *__restrict__ status) {
     if (io.ctl && io.ctl->stale) return;  // lazy re-binning: this step is void
@@ -256,7 +288,11 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     NlWalkSmem<CAP> &S = *reinterpret_cast<NlWalkSmem<CAP> *>(smem_raw);
     const uint32_t tid = threadIdx.x;
-    const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
+    // SORTED: which boid of the CTA's window this thread holds, and its count, come packed from the build
+    // (a CTA without lists keeps the plain assignment: its build may not have got as far as the ranking)
+    const bool ranked = SORTED && !__ldg(nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS + 18);
+    const uint32_t packed = ranked ? __ldg(nl.count + (size_t)blockIdx.x * NL_BLOCK + tid) : 0u;
+    const uint32_t s = io.first + blockIdx.x * NL_BLOCK + (ranked ? packed >> 8 : tid);
     const bool active = s < io.last;
     if (tid == 0) mbar_init(&S.bar, 1);
 
@@ -265,7 +301,7 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     if (active) {
         pi4 = io.pos_s[s];
         vi4 = vel_s[s];
-        n_c = __ldg(nl.count + (s - io.first));
+        n_c = ranked ? (packed & 0xffu) : __ldg(nl.count + (s - io.first));
     }
     // this CTA's list block and the first batch of entries, in flight while the tile is staged
     const uint16_t *const vlp = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + tid;
@@ -385,38 +421,44 @@ size_t nl_cta_tab_elems(uint32_t rows) {
     return (((size_t)rows + NL_BLOCK - 1) / NL_BLOCK) * NL_CTA_WORDS;
 }
 
-int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, bool staged) {
+int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, int form) {
     if (io.last <= io.first) return FP_OK;
     const uint32_t ctas = (io.last - io.first + NL_BLOCK - 1) / NL_BLOCK;
-    if (staged) {
+    if (form == NL_FORM_STAGED || form == NL_FORM_SORTED) {
         const int smem = (int)(sizeof(NlBuildSmem) + sizeof(uint16_t) * NL_STAGE_ROWS * NL_BLOCK);
-        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        nl_build_kernel<true><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+        if (form == NL_FORM_SORTED) {
+            FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            nl_build_kernel<true, true><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+        } else {
+            FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            nl_build_kernel<true, false><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+        }
     } else {
         const int smem = (int)sizeof(NlBuildSmem);
-        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        nl_build_kernel<false><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        nl_build_kernel<false, false><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
     }
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;
 }
 
-template <int CAP, int CTAS>
+template <int CAP, int CTAS, bool SORTED>
 static int launch_nl_walk_as(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io,
                              const NlIO &nl, unsigned *status) {
     const int smem = (int)sizeof(NlWalkSmem<CAP>);
-    auto kern = nl_walk_kernel<CAP, CTAS>;
+    auto kern = nl_walk_kernel<CAP, CTAS, SORTED>;
     FP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<(io.last - io.first + NL_BLOCK - 1) / NL_BLOCK, NL_BLOCK, smem, st>>>(P, g, io, nl, status);
     return FP_OK;
 }
 
 int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, const NlIO &nl,
-                   unsigned *status, bool six_ctas) {
+                   unsigned *status, int form) {
     if (io.last <= io.first) return FP_OK;
-    const int rc = six_ctas ? launch_nl_walk_as<48, 6>(st, P, g, io, nl, status)
-                            : launch_nl_walk_as<NL_CAP, 5>(st, P, g, io, nl, status);
+    const int rc = form == NL_FORM_SIX_CTAS ? launch_nl_walk_as<48, 6, false>(st, P, g, io, nl, status)
+                   : form == NL_FORM_SORTED ? launch_nl_walk_as<NL_CAP, 5, true>(st, P, g, io, nl, status)
+                                            : launch_nl_walk_as<NL_CAP, 5, false>(st, P, g, io, nl, status);
     if (rc) return rc;
     count_launch();
     FP_CUDA(cudaGetLastError());

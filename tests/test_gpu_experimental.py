@@ -2,7 +2,8 @@
 
 FP_WALK_VARIANT=41 selects fp_walk_nl.cu (candidate lists built once per binning)
 instead of the production walk for the steps of a single-GPU grid flock; 42 does the same for
-the slabs of a sharded flock; 43 is 41 with a cheaper build, 44 is 41 at six CTAs per SM.  Neither is the default: 41 was checked on a B200 with the state
+the slabs of a sharded flock; 43 is 41 with a cheaper build, 44 is 41 at six CTAs per SM, 45 is 43 with each CTA's boids
+handed to its threads in order of list length.  Neither is the default: 41 was checked on a B200 with the state
 hashes below (profiles/r1_nl_*.log) when the round's GPU budget was nearly spent, the full
 suites have not run on it, and 42 has not run on hardware at all -- so these checks do not run
 unless asked for.  The variant is read from the environment when the library is first used,
@@ -44,7 +45,7 @@ def _hash(variant, *args):
     return json.loads(r.stdout.strip().splitlines()[-1]), r.stderr
 
 
-@pytest.mark.parametrize("variant", [41, 43, 44])  # 43: staged build; 44: 48-entry lists, six CTAs per SM
+@pytest.mark.parametrize("variant", [41, 43, 44, 45])  # 43: staged build; 44: six CTAs per SM; 45: sorted lanes
 @pytest.mark.parametrize("args", [(200_000, 470.0, 120, 7), (1 << 20, 816.0, 600, 11)])
 def test_runs_agree_bit_for_bit_with_the_production_walk(args, variant):
     a, _ = _hash(31, *args)
