@@ -455,7 +455,14 @@ WalkIO walk_io(fp_flock *f, bool stepping) {
 // length.  42 .. 45 have not run on hardware yet.
 constexpr uint32_t NL_VCAP = 96;  // C3 / C4 density: 34 candidates per boid on average, ~70 at most
 
-int nl_variant();
+int nl_variant() {
+    static const int variant = [] {
+        const char *e = getenv("FP_WALK_VARIANT");
+        return e ? atoi(e) : 0;
+    }();
+    return variant;
+}
+
 int nl_form() {  // which form of the kernels the variant asks for (build and walk alike)
     switch (nl_variant()) {
         case 43: return NL_FORM_STAGED;
@@ -463,14 +470,6 @@ int nl_form() {  // which form of the kernels the variant asks for (build and wa
         case 45: return NL_FORM_SORTED;
         default: return NL_FORM_PLAIN;
     }
-}
-
-int nl_variant() {
-    static const int variant = [] {
-        const char *e = getenv("FP_WALK_VARIANT");
-        return e ? atoi(e) : 0;
-    }();
-    return variant;
 }
 
 bool nl_wanted(const fp_flock *f) {
