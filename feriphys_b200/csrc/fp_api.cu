@@ -131,6 +131,13 @@ void dev_free(T *&p) {
     p = nullptr;
 }
 
+// bookkeeping of the experimental candidate lists: the flock has just been binned
+void nl_binned(fp_flock *f) {
+    f->nl_fresh = true;
+    f->nl_prev_bin_steps = f->nl_bin_steps;
+    f->nl_bin_steps = 0;
+}
+
 int ensure_stage(fp_flock *f, size_t bytes) {
     if (bytes <= f->stage_bytes) return FP_OK;
     if (f->d_stage) cudaFree(f->d_stage);
@@ -424,7 +431,7 @@ int grid_rebin(fp_flock *f) {
     f->bin_valid = true;
     f->plan_left = plan_steps(f, 0.0f, 0.0f);
     ++f->stat_rebins;
-    f->nl_fresh = true;
+    nl_binned(f);
     return FP_OK;
 }
 
@@ -452,7 +459,8 @@ WalkIO walk_io(fp_flock *f, bool stepping) {
 // DESIGN.md 4.2); 42: sharded grid flocks as well (same kernels over the owned slots of a slab);
 // 43: as 41 with the build's stores staged through shared memory; 44: as 41 with 48-entry survivor
 // lists and six CTAs per SM; 45: as 43 with a CTA's boids handed to its threads in order of list
-// length.  42 .. 45 have not run on hardware yet.
+// length; 46: as 41, building only for binnings that live (see nl_prepare).  42 .. 46 have not run
+// on hardware yet.
 constexpr uint32_t NL_VCAP = 96;  // C3 / C4 density: 34 candidates per boid on average, ~70 at most
 
 int nl_variant() {
@@ -474,7 +482,7 @@ int nl_form() {  // which form of the kernels the variant asks for (build and wa
 
 bool nl_wanted(const fp_flock *f) {
     const int variant = nl_variant();
-    const bool on = f->shard ? variant == 42 : (variant >= 41 && variant <= 45);
+    const bool on = f->shard ? variant == 42 : (variant >= 41 && variant <= 46);
     return on && !f->nl_off && f->grid.skin > 0.0f;  // (no skin = a binning per step: nothing to re-use)
 }
 
@@ -522,7 +530,7 @@ int nl_review(fp_flock *f) {
     return FP_OK;
 }
 
-NlIO nl_io(const fp_flock *f) {
+NlIO nl_io(const fp_flock *f, double skins = 1.0) {
     NlIO nl{};
     nl.entries = f->nl_entries;
     nl.count = f->nl_count;
@@ -530,7 +538,8 @@ NlIO nl_io(const fp_flock *f) {
     nl.flag = f->nl_flag;
     nl.vcap = NL_VCAP;
     // every pair within reach while the binning stands was within reach + skin when it was made
-    const double R = (double)reach_of(f->cfg) + (double)f->grid.skin;
+    // (skins = 2: within reach + 2 skin at any other moment of the binning's life)
+    const double R = (double)reach_of(f->cfg) + skins * (double)f->grid.skin;
     nl.m2_wide = nextafterf((float)(R * R * (1.0 + 1e-5)), INFINITY);
     return nl;
 }
@@ -538,12 +547,28 @@ NlIO nl_io(const fp_flock *f) {
 // Called once per step, after the binning / gate and before the walk: builds the lists when the
 // flock has just been binned (by this step, or by a tap since the last step -- either way the
 // positions are still the binned ones) and the lists on hand describe an older binning.
+//
+// Variant 46 (not yet run on hardware) builds only for binnings that live: a caller that hands over
+// a new state every step bins every step, and build + list walk is slower than the production walk
+// alone.  At once when the previous binning served >= 8 steps; otherwise at the binning's SECOND
+// step, from the positions of that moment -- every boid is within skin / 2 of its binned position
+// throughout, hence within skin of where it stands at the build: the cut becomes reach + 2 skin.
 int nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) {
-    if (!nl_wanted(f) || !f->nl_fresh || f->nl_serial == f->stat_rebins) return FP_OK;
+    if (!nl_wanted(f) || f->nl_serial == f->stat_rebins) return FP_OK;
+    double skins = 1.0;
+    if (nl_variant() != 46) {
+        if (!f->nl_fresh) return FP_OK;
+    } else if (f->nl_fresh) {
+        if (f->nl_prev_bin_steps < 8) return FP_OK;  // short-lived so far: see whether a second step comes
+    } else if (f->nl_bin_steps == 1) {
+        skins = 2.0;
+    } else {
+        return FP_OK;
+    }
     int rc = nl_review(f);  // (may turn the lists off)
     if (rc || !nl_wanted(f)) return rc;
     const uint32_t rows = io.last - io.first;
-    if ((rc = nl_ensure(f, rows)) || (rc = launch_nl_build(f->stream, g, io, nl_io(f), nl_form()))) return rc;
+    if ((rc = nl_ensure(f, rows)) || (rc = launch_nl_build(f->stream, g, io, nl_io(f, skins), nl_form()))) return rc;
     f->nl_serial = f->stat_rebins;
     f->nl_built_rows = rows;
     return FP_OK;
@@ -552,6 +577,7 @@ int nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) {
 // the step's walk: on the lists when they describe the standing binning, else the production kernel
 int nl_or_production_walk(fp_flock *f, const GridDesc &g, const WalkIO &io) {
     f->nl_fresh = false;
+    ++f->nl_bin_steps;
     if (nl_wanted(f) && f->nl_serial == f->stat_rebins)
         return launch_nl_walk(f->stream, f->P, g, io, nl_io(f), f->d_status, nl_form());
     return launch_grid_walk(f->stream, f->P, g, TAP_STEP, io, f->d_status, TapOut{});
@@ -674,6 +700,7 @@ int run_tap(fp_flock *f, int tap, const TapOut &out) {
 namespace fp {
 int flock_fit_grid(fp_flock *f) { return fit_grid(f); }
 int flock_nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) { return nl_prepare(f, g, io); }
+void flock_nl_binned(fp_flock *f) { nl_binned(f); }
 int flock_step_walk(fp_flock *f, const GridDesc &g, const WalkIO &io) { return nl_or_production_walk(f, g, io); }
 void flock_select_leads(fp_flock *f) { select_leads(f); }
 int64_t flock_plan_steps(const fp_flock *f, float D, float first_delta) { return plan_steps(f, D, first_delta); }

@@ -61,6 +61,7 @@ struct fp_flock {
     uint32_t nl_built_rows = 0;  // boids of the last build
     uint64_t nl_serial = ~0ull;  // stat_rebins of the binning the lists describe
     bool nl_fresh = false;       // the flock was binned and has not stepped since: lists may be built
+    uint32_t nl_bin_steps = 0, nl_prev_bin_steps = 0;  // steps walked on this binning / on the one before
     bool nl_off = false;         // a list overflowed: production walk until a new state / config arrives
     // staging for host transfers
     void *d_stage = nullptr;

@@ -927,7 +927,7 @@ static int slab_rebin(Shard *s, fp_flock *f) {
     f->steps_since_bin = 0;
     f->plan_left = flock_plan_steps(f, 0.0f, 0.0f);
     ++f->stat_rebins;
-    f->nl_fresh = true;
+    flock_nl_binned(f);
     s->global_valid = false;
     return FP_OK;
 }

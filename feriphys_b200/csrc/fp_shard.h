@@ -11,6 +11,7 @@ void flock_select_leads(fp_flock *f);
 int flock_mark(fp_flock *f);  // timing-hook event
 // experimental candidate lists (fp_walk_nl.cu): build after a binning if wanted; the step's walk
 int flock_nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io);
+void flock_nl_binned(fp_flock *f);  // bookkeeping: the flock has just been binned
 int flock_step_walk(fp_flock *f, const GridDesc &g, const WalkIO &io);  // lists if on hand, else production
 // one all-pairs step launch with the staged / one-phase choice made by measurement
 int flock_allpairs_step(fp_flock *f, const float4 *pos_all, const float4 *vel_all, uint32_t n_all, uint32_t row0,

@@ -97,3 +97,29 @@ def test_candidate_list_cut_keeps_every_pair_that_can_come_into_reach(reach, ski
     assert (then < m2_wide).all()
     # not vacuous: the closest call is within a few percent of the cut
     assert float(then.max()) > 0.9 * float(m2_wide)
+
+
+@pytest.mark.parametrize("reach,skin,extent", [(16.0, 0.11, 300.0), (16.0, 2.0, 500.0), (5.0, 0.6, 90.0)])
+def test_lists_built_mid_binning_need_twice_the_skin(reach, skin, extent):
+    """Variant 46 builds the lists at a binning's second step, from the positions of that moment:
+    both then and later every boid is within skin / 2 of its BINNED position, so a pair within
+    reach later is within reach + 2 skin at the build -- and reach + skin is not enough."""
+    rng = np.random.default_rng(int(reach * 10 + skin * 1000))
+    n = 60000
+    binned = rng.random((n, 3)) * extent
+
+    def drift():
+        d = rng.normal(size=(n, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        return d * (skin / 2) * np.where(rng.random((n, 1)) < 0.5, 1.0, rng.random((n, 1)))
+
+    at_build = (binned + drift()).astype(f32)
+    later = (binned + drift()).astype(f32)
+    pairs = cKDTree(later.astype(np.float64)).query_pairs(reach * (1 + 1e-6), output_type="ndarray")
+    i, j = pairs[:, 0], pairs[:, 1]
+    d = (at_build[j] - at_build[i]).astype(np.float64)
+    m2 = (d * d).sum(axis=1)
+    wide = lambda skins: (reach + skins * skin) ** 2 * (1.0 + 1e-5)
+    assert (m2 * (1 + 1e-6) < wide(2.0)).all()
+    if skin >= 0.5:
+        assert (m2 >= wide(1.0)).any()
