@@ -1,5 +1,7 @@
-// fp_walk_nl.cu -- K3 with standing candidate lists (EXPERIMENTAL: FP_WALK_VARIANT=41,
-// single GPU, TAP_STEP only; not the default and not yet timed on hardware).
+// fp_walk_nl.cu -- K3 with standing candidate lists (EXPERIMENTAL, TAP_STEP only, not the
+// default: FP_WALK_VARIANT=41 .. 46, see nl_prepare in fp_api.cu).  The plain form (41) has run on
+// a B200: bit-identical to the production walk in every run compared, C4 5.66 -> 3.85 ms/step
+// (profiles/r1_nl_*.log); the other forms are written but have not run yet.
 //
 // With lazy re-binning a binning stands for ~20 steps, yet the production
 // walk (fp_walk.cu) pre-gates all ~160 candidates of a boid's 27 home cells in every one of
