@@ -456,7 +456,13 @@ def run_ours(args, w, rank, world, local_rank):
                 traffic_src = t["source"]
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "grid_walk3_kernel<TAP_STEP> (TMA-staged 27-cell walk + extras + Euler)",
+        variant = os.environ.get("FP_WALK_VARIANT", "")
+        lists = variant in ("41", "43", "44", "45", "46") and world == 1 or variant == "42"
+        if lists:   # experimental candidate-list walk: no ncu capture of it yet
+            traffic, traffic_src = None, None
+        roofline = {"bound": "hbm", "kernel": (f"nl_walk_kernel (FP_WALK_VARIANT={variant}: walk on standing candidate lists)"
+                                               if lists else
+                                               "grid_walk3_kernel<TAP_STEP> (TMA-staged 27-cell walk + extras + Euler)"),
                     "achieved": 64.0 * n_local / infl_s / 1e9, "peak": hbm, "unit": "GB/s",
                     "algorithmic_bytes_per_boid": 64, "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": 64 * int(n_local), "peak_source": peak_src,
