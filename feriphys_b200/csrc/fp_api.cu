@@ -306,6 +306,24 @@ int fit_grid(fp_flock *f) {
     // at most zspan slices apart (the 1/512 margin of the edge covers the rounding of zspan / cell)
     g.inv_cell_z = (float)((double)g.zspan / cell);
     for (int a = 0; a < 3; ++a) g.origin[a] = lo[a];
+    {
+        // FP_GRID_CENTER=1 (tuning, not yet run on hardware): centre the grid on the flock instead of
+        // anchoring it at the minimum corner.  When the extent is a hair over a whole number of cells
+        // the anchored grid ends in a sliver row holding a handful of boids spread over all of z; the
+        // CTA that holds them has nine intervals spanning whole rows, overflows the tile and takes the
+        // slow global-memory path (C3 at skin 0.28: 53 of 8192 CTAs, emulated on the CPU and seen on
+        // the GPU; 0 when centred: every edge cell is then at least half a cell wide).
+        static const bool center = [] {
+            const char *e = getenv("FP_GRID_CENTER");
+            return e && atoi(e) != 0;
+        }();
+        if (center)
+            for (int a = 0; a < 3; ++a) {
+                const double edge = a == 2 ? cell / g.zspan : cell;
+                const double slack = (double)g.dim[a] * edge - ((double)hi[a] - (double)lo[a]);
+                if (slack > 0.0) g.origin[a] = (float)((double)lo[a] - 0.5 * slack);
+            }
+    }
     uint32_t bits = 1;
     while ((1ull << bits) < g.ncells) ++bits;
     g.key_bits = bits;

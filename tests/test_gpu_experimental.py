@@ -86,3 +86,13 @@ def test_sharded_suite_passes_on_candidate_lists():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800, env=_env(42), cwd=ROOT)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     assert "candidate lists on" in r.stderr, "the variant was never used"
+
+
+def test_grid_suite_passes_on_a_centred_grid():
+    # FP_GRID_CENTER=1 (fit_grid): the grid centred on the flock, no sliver rows; any origin must
+    # give the oracle's neighbour sets and, on the library's listing, its bits
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+           os.path.join(ROOT, "tests", "test_gpu_rebin.py"), os.path.join(ROOT, "tests", "test_gpu_grid.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800, env=dict(os.environ, FP_GRID_CENTER="1"),
+                       cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
