@@ -521,7 +521,7 @@ int nl_ensure(fp_flock *f, uint32_t rows) {
     int rc;
     const size_t entries = nl_entries_elems(cap, NL_VCAP);
     if ((rc = dev_alloc(&f->nl_entries, entries)) || (rc = dev_alloc(&f->nl_count, (size_t)cap + 128)) ||
-        (rc = dev_alloc(&f->nl_cta_tab, nl_cta_tab_elems(cap))) || (rc = dev_alloc(&f->nl_flag, 1)))
+        (rc = dev_alloc(&f->nl_cta_tab, nl_cta_tab_elems(cap))) || (rc = dev_alloc(&f->nl_flag, 4)))
         return rc;
     FP_CUDA(cudaMemsetAsync(f->nl_entries, 0, entries * sizeof(uint16_t), f->stream));
     FP_CUDA(cudaMemsetAsync(f->nl_flag, 0, sizeof(unsigned), f->stream));
@@ -586,7 +586,10 @@ int nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) {
     int rc = nl_review(f);  // (may turn the lists off)
     if (rc || !nl_wanted(f)) return rc;
     const uint32_t rows = io.last - io.first;
-    if ((rc = nl_ensure(f, rows)) || (rc = launch_nl_build(f->stream, g, io, nl_io(f, skins), nl_form()))) return rc;
+    const float sort_params[3] = {f->P.m2_cut_hi, f->P.fov_kh, f->P.fov_kl};
+    if ((rc = nl_ensure(f, rows)) ||
+        (rc = launch_nl_build(f->stream, g, io, nl_io(f, skins), nl_form(), sort_params)))
+        return rc;
     f->nl_serial = f->stat_rebins;
     f->nl_built_rows = rows;
     return FP_OK;

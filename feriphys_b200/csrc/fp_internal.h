@@ -166,7 +166,8 @@ struct NlIO {
     uint16_t *entries;   // [cta][vcap][128]: tile offsets (row << 12 | offset) of the candidates in reach + skin
     uint16_t *count;     // [slot - first]: entries of each boid (NL_FORM_SORTED: [cta * 128 + thread], boid << 8 | entries)
     uint32_t *cta_tab;   // [cta][20]: the nine staged intervals of each CTA, [18] != 0: this CTA has no lists
-    unsigned *flag;      // CTAs the last build left without lists (tile or list overflow)
+    unsigned *flag;      // [0]: CTAs the last build left without lists (tile or list overflow);
+                         // [1..3]: NL_FORM_SORTED, bits of DevParams' m2_cut_hi, fov_kh, fov_kl
     uint32_t vcap;       // list capacity, a multiple of 4
     float m2_wide;       // build cut: (reach + skin)^2 (1 + 1e-5)
 };
@@ -178,7 +179,9 @@ size_t nl_cta_tab_elems(uint32_t rows);
 // writes whole rows; SIX_CTAS (44) walks with 48-entry survivor lists at six CTAs per SM; SORTED (45)
 // hands a CTA's boids to its threads in order of list length (build and walk must agree on it).
 enum { NL_FORM_PLAIN = 0, NL_FORM_STAGED = 1, NL_FORM_SIX_CTAS = 2, NL_FORM_SORTED = 3 };
-int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, int form = NL_FORM_PLAIN);
+// sort_params (NL_FORM_SORTED): DevParams' m2_cut_hi, fov_kh, fov_kl
+int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, int form = NL_FORM_PLAIN,
+                    const float sort_params[3] = nullptr);
 // a step (TAP_STEP) on the standing lists; same result as launch_grid_walk
 int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, const NlIO &nl,
                    unsigned *status, int form = NL_FORM_PLAIN);

@@ -95,9 +95,9 @@ constexpr int NL_STAGE_ROWS = 96;  // STAGED: rows of the shared-memory staging 
 // run on hardware): entries are collected in shared memory, [entry][thread], and the CTA's
 // block is written row by row, 256 contiguous bytes per row.
 // SORTED (needs STAGED; variant 45, not yet run on hardware): the CTA's 128 boids are handed to its
-// threads in descending order of list length, so that the lanes of a warp walk lists of similar
-// length (candidate counts are Poisson, 35 +- 6: unsorted, a warp runs as long as its longest
-// list, ~46 entries).  Lane l of the CTA then holds boid (count[cta * 128 + l] >> 8) of the
+// threads in descending order of the work they will cost the walk, so that the lanes of a warp
+// finish together (unsorted, a warp runs as long as its longest gate list, ~44 entries against 34
+// on average, and its longest drain list, ~24 against 16).  Lane l of the CTA then holds boid (count[cta * 128 + l] >> 8) of the
 // CTA's slot window, with its list in column l; the count stays in the low byte.  Any
 // assignment of boids to threads gives the same result: each boid still sums its own
 // contributions in slot order.
@@ -123,9 +123,19 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     float4 pi4 = make_float4(0, 0, 0, 0);
     bool work = false;
     int cx = 0, cy = 0, cz = 0;
+    float2 vhx = make_float2(0, 0), vhy = vhx, vhz = vhx;  // SORTED: direction of flight, both halves
     if (active) {
         pi4 = io.pos_s[s];
-        work = __float_as_uint(io.vel_s[s].w) == 0u;  // not a ghost record
+        if (SORTED) {
+            const float4 vi4 = io.vel_s[s];
+            work = __float_as_uint(vi4.w) == 0u;
+            const float inv = rsqrtf(fmaf(vi4.z, vi4.z, fmaf(vi4.y, vi4.y, vi4.x * vi4.x)));  // a prediction: no need to be exact
+            vhx = make_float2(vi4.x * inv, vi4.x * inv);
+            vhy = make_float2(vi4.y * inv, vi4.y * inv);
+            vhz = make_float2(vi4.z * inv, vi4.z * inv);
+        } else {
+            work = __float_as_uint(io.vel_s[s].w) == 0u;  // not a ghost record
+        }
         home_cell(g, __ldg(io.home + (s - io.first)), cx, cy, cz);
     }
     // the nine slot ranges of this boid, rows in ascending key order (dx outer, dy inner)
@@ -189,6 +199,11 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     uint16_t *const stg = reinterpret_cast<uint16_t *>(smem_raw + sizeof(NlBuildSmem)) + tid;  // STAGED: same layout
     const uint32_t vcap = STAGED ? min(nl.vcap, (uint32_t)NL_STAGE_ROWS) : nl.vcap;
     uint32_t w = 0;  // entries found
+    uint32_t pred = 0;  // SORTED: entries that would pass the walk's pre-gate as things stand now
+    // (what that takes of DevParams -- m2_cut_hi, fov_kh, fov_kl -- sits behind the counter in nl.flag)
+    const float sp_cut = SORTED ? __uint_as_float(__ldg(nl.flag + 1)) : 0.0f;
+    const float sp_kh = SORTED ? __uint_as_float(__ldg(nl.flag + 2)) : 0.0f;
+    const float sp_kl = SORTED ? __uint_as_float(__ldg(nl.flag + 3)) : 0.0f;
     const float2 nsx = make_float2(-pi4.x, -pi4.x), nsy = make_float2(-pi4.y, -pi4.y),
                  nsz = make_float2(-pi4.z, -pi4.z);
 #pragma unroll 1
@@ -211,11 +226,19 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
             const float2 m01 = __ffma2_rn(dz01, dz01, __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01)));
             const float2 m23 = __ffma2_rn(dz23, dz23, __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23)));
             const float mm[4] = {m01.x, m01.y, m23.x, m23.y};
+            float ss[4] = {0, 0, 0, 0};
+            if (SORTED) {  // the walk's conservative FOV test (fp_walk.cu), for the prediction
+                const float2 q01 = __ffma2_rn(vhz, dz01, __ffma2_rn(vhy, dy01, __fmul2_rn(vhx, dx01)));
+                const float2 q23 = __ffma2_rn(vhz, dz23, __ffma2_rn(vhy, dy23, __fmul2_rn(vhx, dx23)));
+                ss[0] = q01.x * fabsf(q01.x); ss[1] = q01.y * fabsf(q01.y);
+                ss[2] = q23.x * fabsf(q23.x); ss[3] = q23.y * fabsf(q23.y);
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if ((live >> u & 1u) && !(mm[u] >= nl.m2_wide) && T + u != t_self) {  // NaN never drops
                     if (w < vcap) (STAGED ? stg : out)[(size_t)w * NL_BLOCK] = (uint16_t)(tag | (T + u));
                     ++w;
+                    if (SORTED && !(mm[u] >= sp_cut) && !(ss[u] < sp_kh * mm[u] && ss[u] > sp_kl * mm[u])) ++pred;
                 }
         };
         if (len) {
@@ -233,25 +256,43 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     if (__any_sync(0xffffffffu, w > vcap) && (tid & 31) == 0) nl_no_lists(nl, tab);
     if (STAGED && SORTED) {
         static_assert(!SORTED || STAGED, "the sorted layout is written from the staging block");
-        __shared__ uint32_t hist[NL_STAGE_ROWS + 1];  // threads per list length, then running ranks
+        // Sort key: the work a boid will cost the walk -- mostly its drain (entries that survive the
+        // pre-gate: predicted from the velocities of this moment, the field of view turns slowly),
+        // a little its gate (all entries).  Emulated on a C3-density flock: sorting by
+        // this key takes ~14 % off the gate + drain work of a warp, by the list length alone 9 %.
+        constexpr int NKEY = 128;
+        __shared__ uint32_t hist[NKEY];  // threads per key, then running ranks
         __shared__ uint32_t wmax_s;
         const uint32_t c = min(w, vcap);
-        if (tid <= (uint32_t)NL_STAGE_ROWS) hist[tid] = 0u;
+        const uint32_t key = min(pred + c / 4u, (uint32_t)NKEY - 1u);
+        hist[tid] = 0u;  // (NKEY == NL_BLOCK)
+        if (tid == 0) wmax_s = 0u;
         __syncthreads();
-        atomicAdd(&hist[c], 1u);
+        atomicAdd(&hist[key], 1u);
+        atomicMax(&wmax_s, c);
         __syncthreads();
-        if (tid == 0) {  // first rank of each length, longest lists first
-            uint32_t run = 0, longest = 0;
-            for (int len = NL_STAGE_ROWS; len >= 0; --len) {
-                const uint32_t t = hist[len];
-                if (t && !longest) longest = (uint32_t)len;
-                hist[len] = run;
-                run += t;
+        if (tid < 32) {  // first rank of each key, costliest first: lane l owns keys 127 - 4 l .. 124 - 4 l
+            uint32_t t[4], sum = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                t[u] = hist[NKEY - 1 - (4 * tid + u)];
+                sum += t[u];
             }
-            wmax_s = longest;
+            uint32_t inc = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+                if ((int)tid >= off) inc += o;
+            }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                hist[NKEY - 1 - (4 * tid + u)] = run;
+                run += t[u];
+            }
         }
         __syncthreads();
-        const uint32_t rank = atomicAdd(&hist[c], 1u);  // (order within one length: whoever comes first)
+        const uint32_t rank = atomicAdd(&hist[key], 1u);  // (order within one key: whoever comes first)
         nl.count[(size_t)blockIdx.x * NL_BLOCK + rank] = (uint16_t)(c | (tid << 8));
         uint16_t *const col = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + rank;
         const uint32_t rows = wmax_s;
@@ -423,12 +464,15 @@ size_t nl_cta_tab_elems(uint32_t rows) {
     return (((size_t)rows + NL_BLOCK - 1) / NL_BLOCK) * NL_CTA_WORDS;
 }
 
-int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, int form) {
+int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, int form,
+                    const float sort_params[3]) {
     if (io.last <= io.first) return FP_OK;
     const uint32_t ctas = (io.last - io.first + NL_BLOCK - 1) / NL_BLOCK;
     if (form == NL_FORM_STAGED || form == NL_FORM_SORTED) {
         const int smem = (int)(sizeof(NlBuildSmem) + sizeof(uint16_t) * NL_STAGE_ROWS * NL_BLOCK);
         if (form == NL_FORM_SORTED) {
+            // (pageable source: the copy has left the host buffer when the call returns)
+            FP_CUDA(cudaMemcpyAsync(nl.flag + 1, sort_params, 3 * sizeof(float), cudaMemcpyHostToDevice, st));
             FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             nl_build_kernel<true, true><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
         } else {

@@ -35,7 +35,8 @@ def kernel_hashes():
             name, body = part.split("\n", 1)
             # anonymous-namespace symbols carry a per-file hash of the source path: drop it
             name = re.sub(r"_GLOBAL__N__[0-9a-f]+_\d+_(\w+?)_cu_[0-9a-f]+", r"anon_\1", name.strip())
-            lines = [ln.rstrip() for ln in body.splitlines() if ln.strip()]
+            # (cuobjdump pads its columns to the longest line of the whole object: collapse the blanks)
+            lines = [re.sub(r"\s+", " ", ln).strip() for ln in body.splitlines() if ln.strip()]
             out[f"{obj}:{name}"] = hashlib.sha256("\n".join(lines).encode()).hexdigest()
     return out
 
