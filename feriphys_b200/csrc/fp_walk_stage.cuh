@@ -1,9 +1,9 @@
-// fp_walk_stage.cuh -- building blocks of a shared-memory staged walk kernel: the TMA
-// bulk-copy / mbarrier primitives and the drain, i.e. the exact force phase over a
-// per-thread survivor list.  Used by fp_walk_nl.cu.  The production kernel in fp_walk.cu
-// still carries its own inlined copy of the same code: folding it onto this header changes
-// ptxas' register allocation of that kernel (compared SASS to SASS), so the merge waits
-// until it can be timed on a B200.
+// fp_walk_stage.cuh -- building blocks of the shared-memory staged walk kernels: the TMA
+// bulk-copy / mbarrier primitives (fp_walk.cu, fp_walk_nl.cu) and the drain, i.e. the exact force
+// phase over a per-thread survivor list (fp_walk_nl.cu).  The production kernel in fp_walk.cu
+// still carries its own inlined copy of the drain: folding it onto drain_list changes ptxas'
+// register allocation of that kernel (tools/sass_pins.py), so the merge waits until it can be
+// timed on a B200.
 #pragma once
 
 #include "fp_grid.cuh"
