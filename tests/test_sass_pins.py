@@ -18,5 +18,7 @@ def test_measured_kernels_are_unchanged():
     if not os.path.isdir(os.path.join(ROOT, "feriphys_b200", "csrc", "_build")):
         pytest.skip("library not built in-tree")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_pins.py")], capture_output=True, text=True)
+    if r.returncode == 2:
+        pytest.skip(r.stdout.strip())
     assert r.returncode == 0, ("kernels differ from the build last run on hardware -- re-validate on a B200, then "
                                "`python tools/sass_pins.py --record`:\n" + r.stdout[-3000:] + r.stderr[-1000:])

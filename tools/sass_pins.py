@@ -41,17 +41,28 @@ def kernel_hashes():
     return out
 
 
+def nvcc_version():
+    out = subprocess.run(["nvcc", "--version"], capture_output=True, text=True).stdout
+    m = re.search(r"release [\d.]+, V([\d.]+)", out)
+    return m.group(1) if m else "unknown"
+
+
 def main():
-    cur = kernel_hashes()
     if "--record" in sys.argv:
+        cur = kernel_hashes()
         pins = {k: v for k, v in cur.items() if not UNPINNED.search(k)}
         with open(PINS, "w") as fh:
             json.dump({"note": "SASS hashes of the kernels as last run on a B200 (tools/sass_pins.py)",
-                       "kernels": pins}, fh, indent=1, sort_keys=True)
+                       "nvcc": nvcc_version(), "kernels": pins}, fh, indent=1, sort_keys=True)
         print(f"recorded {len(pins)} kernels ({len(cur) - len(pins)} not yet run on hardware left out)")
         return 0
     with open(PINS) as fh:
-        pins = json.load(fh)["kernels"]
+        doc = json.load(fh)
+    pins = doc["kernels"]
+    if doc.get("nvcc") not in (None, nvcc_version()):
+        print(f"pins were recorded with nvcc {doc['nvcc']}, this is {nvcc_version()}: another compiler, other code")
+        return 2
+    cur = kernel_hashes()
     bad = [k for k, v in pins.items() if cur.get(k) != v]
     for k in bad:
         print(("CHANGED " if k in cur else "MISSING ") + k)
