@@ -477,8 +477,8 @@ WalkIO walk_io(fp_flock *f, bool stepping) {
 // DESIGN.md 4.2); 42: sharded grid flocks as well (same kernels over the owned slots of a slab);
 // 43: as 41 with the build's stores staged through shared memory; 44: as 41 with 48-entry survivor
 // lists and six CTAs per SM; 45: as 43 with a CTA's boids handed to its threads in order of list
-// length; 46: as 41, building only for binnings that live (see nl_prepare).  42 .. 46 have not run
-// on hardware yet.
+// length; 46: as 41, building only for binnings that live (see nl_prepare); 47: 43 .. 46 together.
+// 42 .. 47 have not run on hardware yet.
 constexpr uint32_t NL_VCAP = 96;  // C3 / C4 density: 34 candidates per boid on average, ~70 at most
 
 int nl_variant() {
@@ -493,14 +493,15 @@ int nl_form() {  // which form of the kernels the variant asks for (build and wa
     switch (nl_variant()) {
         case 43: return NL_FORM_STAGED;
         case 44: return NL_FORM_SIX_CTAS;
-        case 45: return NL_FORM_SORTED;
+        case 45: return NL_FORM_SORTED | NL_FORM_STAGED;
+        case 47: return NL_FORM_SORTED | NL_FORM_STAGED | NL_FORM_SIX_CTAS;
         default: return NL_FORM_PLAIN;
     }
 }
 
 bool nl_wanted(const fp_flock *f) {
     const int variant = nl_variant();
-    const bool on = f->shard ? variant == 42 : (variant >= 41 && variant <= 46);
+    const bool on = f->shard ? variant == 42 : (variant >= 41 && variant <= 47);
     return on && !f->nl_off && f->grid.skin > 0.0f;  // (no skin = a binning per step: nothing to re-use)
 }
 
@@ -574,7 +575,7 @@ NlIO nl_io(const fp_flock *f, double skins = 1.0) {
 int nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) {
     if (!nl_wanted(f) || f->nl_serial == f->stat_rebins) return FP_OK;
     double skins = 1.0;
-    if (nl_variant() != 46) {
+    if (nl_variant() != 46 && nl_variant() != 47) {
         if (!f->nl_fresh) return FP_OK;
     } else if (f->nl_fresh) {
         if (f->nl_prev_bin_steps < 8) return FP_OK;  // short-lived so far: see whether a second step comes

@@ -178,7 +178,8 @@ size_t nl_cta_tab_elems(uint32_t rows);
 // are written but have not run yet: STAGED (43) collects the build's entries in shared memory and
 // writes whole rows; SIX_CTAS (44) walks with 48-entry survivor lists at six CTAs per SM; SORTED (45)
 // hands a CTA's boids to its threads in order of list length (build and walk must agree on it).
-enum { NL_FORM_PLAIN = 0, NL_FORM_STAGED = 1, NL_FORM_SIX_CTAS = 2, NL_FORM_SORTED = 3 };
+// (bit flags: 47 combines them; SORTED implies STAGED)
+enum { NL_FORM_PLAIN = 0, NL_FORM_STAGED = 1, NL_FORM_SIX_CTAS = 2, NL_FORM_SORTED = 4 };
 // sort_params (NL_FORM_SORTED): DevParams' m2_cut_hi, fov_kh, fov_kl
 int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, int form = NL_FORM_PLAIN,
                     const float sort_params[3] = nullptr);

@@ -468,9 +468,9 @@ int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const 
                     const float sort_params[3]) {
     if (io.last <= io.first) return FP_OK;
     const uint32_t ctas = (io.last - io.first + NL_BLOCK - 1) / NL_BLOCK;
-    if (form == NL_FORM_STAGED || form == NL_FORM_SORTED) {
+    if (form & (NL_FORM_STAGED | NL_FORM_SORTED)) {
         const int smem = (int)(sizeof(NlBuildSmem) + sizeof(uint16_t) * NL_STAGE_ROWS * NL_BLOCK);
-        if (form == NL_FORM_SORTED) {
+        if (form & NL_FORM_SORTED) {
             // (pageable source: the copy has left the host buffer when the call returns)
             FP_CUDA(cudaMemcpyAsync(nl.flag + 1, sort_params, 3 * sizeof(float), cudaMemcpyHostToDevice, st));
             FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -502,9 +502,11 @@ static int launch_nl_walk_as(cudaStream_t st, const DevParams &P, const GridDesc
 int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, const NlIO &nl,
                    unsigned *status, int form) {
     if (io.last <= io.first) return FP_OK;
-    const int rc = form == NL_FORM_SIX_CTAS ? launch_nl_walk_as<48, 6, false>(st, P, g, io, nl, status)
-                   : form == NL_FORM_SORTED ? launch_nl_walk_as<NL_CAP, 5, true>(st, P, g, io, nl, status)
-                                            : launch_nl_walk_as<NL_CAP, 5, false>(st, P, g, io, nl, status);
+    const bool six = form & NL_FORM_SIX_CTAS, sorted = form & NL_FORM_SORTED;
+    const int rc = six ? (sorted ? launch_nl_walk_as<48, 6, true>(st, P, g, io, nl, status)
+                                 : launch_nl_walk_as<48, 6, false>(st, P, g, io, nl, status))
+                       : (sorted ? launch_nl_walk_as<NL_CAP, 5, true>(st, P, g, io, nl, status)
+                                 : launch_nl_walk_as<NL_CAP, 5, false>(st, P, g, io, nl, status));
     if (rc) return rc;
     count_launch();
     FP_CUDA(cudaGetLastError());

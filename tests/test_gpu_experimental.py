@@ -45,8 +45,8 @@ def _hash(variant, *args):
     return json.loads(r.stdout.strip().splitlines()[-1]), r.stderr
 
 
-# 43: staged build; 44: six CTAs per SM; 45: sorted lanes; 46: lists only for binnings that live
-@pytest.mark.parametrize("variant", [41, 43, 44, 45, 46])
+# 43: staged build; 44: six CTAs per SM; 45: sorted lanes; 46: lists only for binnings that live; 47: all
+@pytest.mark.parametrize("variant", [41, 43, 44, 45, 46, 47])
 @pytest.mark.parametrize("args", [(200_000, 470.0, 120, 7), (1 << 20, 816.0, 600, 11)])
 def test_runs_agree_bit_for_bit_with_the_production_walk(args, variant):
     a, _ = _hash(31, *args)
