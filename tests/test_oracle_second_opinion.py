@@ -248,3 +248,34 @@ def test_steering_agrees_bit_for_bit(orc):
         assert np.array_equal(bits(ours), bits(theirs)), (p, v, ours, theirs)
         n_steer += bool((ours != 0).any())
     assert n_steer > 100
+
+
+def test_whole_step_agrees_bit_for_bit(orc):
+    """Simulation::step (flocking.rs:97-122): a = (((boids + leads) + attractors) + bbox) + steering,
+    or steering alone when it overrides; p' = p + dt * v, v' = v + dt * a, from the old state only."""
+    rng = np.random.default_rng(9)
+    n, extent = 250, 40.0
+    st = np.concatenate([rng.uniform(0, extent, (n, 3)), rng.uniform(-3, 3, (n, 3))], axis=1).astype(f32)
+    leads = [[5, 5, 5, 1, 0, 0, 10], [20, 9, 2, 0, 1, 0, 10]]
+    attractors = [[3, 3, 3, 5], [18, 1, 2, -4]]
+    obstacles = np.array([[60, 20, 20, 6], [-25, 20, 20, 9]], f32)      # outside the flock: nobody is inside a sphere
+    for i in range(0, n, 5):                                            # every fifth boid heads for one, fast
+        aim = obstacles[i % 2, :3] + rng.normal(size=3).astype(f32) * f32(3)
+        st[i, 3:] = (aim - st[i, :3]) / np.linalg.norm(aim - st[i, :3]) * f32(25)
+    bbox = [-1, extent + 1, -1, extent + 1, -1, extent + 1]
+    sc = Scene(leads=leads, attractors=attractors, obstacles=obstacles, bbox=bbox)
+    for overrides in (0, 1):
+        cfg = orc.default_config(steering_overrides=overrides)
+        with np.errstate(all="ignore"):
+            steer = np.stack([steering(cfg, obstacles, st[i, :3], st[i, 3:]) for i in range(n)]).astype(f32)
+            if overrides:
+                a = steer
+            else:
+                a = (((accel_from_boids(cfg, st) + accel_from_leads(cfg, st, leads)) + accel_from_attractors(st, attractors))
+                     + accel_from_bbox(st, bbox)) + steer
+        dt = f32(cfg.dt)
+        exp = np.concatenate([st[:, :3] + dt * st[:, 3:], st[:, 3:] + dt * a], axis=1).astype(f32)
+        got, flags = orc.step(cfg, sc, st)
+        assert not flags.any()
+        assert np.array_equal(bits(exp), bits(got))
+        assert (steer != 0).any()
