@@ -3,14 +3,15 @@
 grid_keys do (x-slowest keys, z slices), forms each 128-boid CTA's nine interval unions and reports
 the CTAs whose total exceeds the 1904-entry tile (they take the slow global-memory path).
     python tools/tile_emulation.py [skin]           # grid anchored at the minimum corner
+    N=4194304 EXTENT=1296 python tools/tile_emulation.py 0.33   # another flock (C5)
     CENTER=1 python tools/tile_emulation.py [skin]  # grid centred on the flock (FP_GRID_CENTER=1)
 Positions advance ballistically (p0 + t v0): enough to show the structural cause (sliver rows)."""
-import sys, numpy as np
+import os, sys, numpy as np
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 from feriphys_b200 import synth
 f32=np.float32
-n=1<<20; extent=816.0
-st=synth.uniform_flock(n, extent, seed=11)
+n=int(os.environ.get('N', 1<<20)); extent=float(os.environ.get('EXTENT', 816.0))
+st=synth.uniform_flock(n, extent, seed=int(os.environ.get('SEED', 11)))
 p0=st[:,:3].astype(np.float64); v0=st[:,3:].astype(np.float64)
 reach=16.0; skin=float(sys.argv[1]) if len(sys.argv)>1 else 0.2763
 cell=reach*(1+1/512)+skin; zspan=4
