@@ -25,8 +25,10 @@ for w in c4 c3 c5; do
     FP_WALK_VARIANT=$v python bench.py --workload $w --no-cpu-baseline > $O/r2_bench_${w}_v$v.json 2>> $O/r2.err
   done
 done
-for v in 31 41; do   # the grid centred on the flock (no sliver rows): C3 at the automatic skin
-  FP_GRID_CENTER=1 FP_WALK_VARIANT=$v python bench.py --workload c3 --no-cpu-baseline --no-e2e > $O/r2_bench_c3_centred_v$v.json 2>> $O/r2.err
+for w in c3 c5; do   # the grid centred on the flock (no sliver rows; C5 has 139 sliver-row CTAs when anchored)
+  for v in 31 41; do
+    FP_GRID_CENTER=1 FP_WALK_VARIANT=$v python bench.py --workload $w --no-cpu-baseline --no-e2e > $O/r2_bench_${w}_centred_v$v.json 2>> $O/r2.err
+  done
 done
 # 3. launch list and full captures of the two new kernels (source page: tools/ncu_source.py)
 FP_WALK_VARIANT=41 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
