@@ -62,6 +62,10 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="cpu_baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--numerics", default=None, choices=["exact", "fast"],
+                    help="arithmetic of the forces (default: the library's default)")
+    ap.add_argument("--no-alt", action="store_true", help="skip the comparison run with the other numerics")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled parity check against the oracle")
     return ap.parse_args()
 
 
@@ -299,6 +303,90 @@ def config_block(w, args, world):
 
 
 # ---- our arm -----------------------------------------------------------------------------
+def parity_check(sim, w, rank, rows=2048):
+    """Sampled parity of the state the bench ends on, outside the timed region: the library's
+    neighbour sets and accelerations (collective taps on a sharded flock) against the oracle run
+    on the same state on rank 0.  -> dict for the JSON line (None on the other ranks)."""
+    state = sim.read_state()                      # global state, caller order (every rank)
+    n = len(state)
+    grid = w["method_resolved"] == "grid" or n > 200_000
+    half = max(1, min(rows, n) // 2)
+    wins = [(0, half), (n - half, n)] if n > 2 * half else [(0, n)]
+    gc, gh = sim.read_neighbors()
+    ga = sim.read_accel()
+    if rank != 0:
+        return None
+    import ctypes as C
+    from oracle_lib import Scene, oracle
+    orc = oracle()
+    cfg = orc.default_config(**w["cfg"])
+    t = w["tables"]
+    leads = getattr(sim, "_lead_rows")()
+    sc = Scene(leads=leads if len(leads) else None, attractors=t.get("attractors"),
+               obstacles=t.get("obstacles"), bbox=t.get("bbox"))
+    threads = os.cpu_count() or 1
+    mism, worst, nrows = 0, 0.0, 0
+    g = orc.lib.orc_grid_build(C.byref(cfg), n, state.ctypes.data_as(C.c_void_p)) if grid else None
+    scs = sc.struct()
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    try:
+        for lo, hi in wins:
+            m = hi - lo
+            rc, rh = np.zeros(m, np.uint32), np.zeros(m, np.uint64)
+            ra = np.zeros((m, 3), np.float32)
+            if grid:
+                orc.lib.orc_grid_neighbors_rows(g, C.byref(cfg), n, P(state), lo, hi, P(rc), P(rh), threads)
+                orc.lib.orc_grid_accel_rows(g, C.byref(cfg), C.byref(scs), n, P(state), lo, hi, P(ra), None, None,
+                                            threads)
+            else:
+                orc.lib.orc_neighbors_rows(C.byref(cfg), n, P(state), lo, hi, P(rc), P(rh), None, 0, threads)
+                orc.lib.orc_accel_rows(C.byref(cfg), C.byref(scs), n, P(state), lo, hi, P(ra), None, None, threads)
+            mism += int(np.count_nonzero((gc[lo:hi] != rc) | (gh[lo:hi] != rh)))
+            num = np.linalg.norm(ga[lo:hi].astype(np.float64) - ra.astype(np.float64), axis=1)
+            den = np.maximum(np.linalg.norm(ra.astype(np.float64), axis=1), 1e-3)
+            worst = max(worst, float((num / den).max()))
+            nrows += m
+    finally:
+        if g is not None:
+            orc.lib.orc_grid_free(g)
+    return {"rows": nrows, "neighbor_mismatches": mism, "max_rel_accel": worst, "accel_bar": 1e-5,
+            "oracle": "grid-accelerated (bit-identical to the literal loops)" if grid else "literal O(N) rows",
+            "state": "the state the run ended on (after warm-up, timed steps and the e2e legs)"}
+
+
+def timed_windows(sim, K, barrier, reduce_max, grid, budget_s=25.0):
+    """K-step windows, each bracketed by a barrier and timed with CUDA events on the library's
+    stream (max over ranks), repeated until >= 1 s of device time has been timed and -- on the grid
+    path -- >= 3 binnings fell inside.  -> (windows, totals)"""
+    wins, tot_s, tot_steps, bins, sort_ms, infl_ms, seen, replay = [], 0.0, 0, 0, 0.0, 0.0, 0, 0
+    t_start = time.perf_counter()
+    while True:
+        rb0 = sim.rebin_info() if grid else None
+        barrier()
+        sim.timing_begin()
+        t0 = time.perf_counter()
+        sim.step_many(K)
+        nst, span_ms, so, inf = sim.timing_end()          # synchronises this rank's stream
+        wall = time.perf_counter() - t0
+        rb1 = sim.rebin_info() if grid else None
+        dev_s, wall_s = reduce_max(span_ms / 1e3, wall)
+        b = (rb1[2] - rb0[2]) if grid else 0
+        wins.append({"ms_per_step": 1e3 * dev_s / K, "binnings": int(b), "wall_ms": 1e3 * wall_s,
+                     "device_span_ms_this_rank": span_ms})
+        tot_s += dev_s
+        tot_steps += K
+        bins += b
+        sort_ms += so
+        infl_ms += inf
+        seen += max(1, nst)
+        replay += (rb1[3] - rb0[3]) if grid else 0
+        enough = tot_s >= 1.0 and (not grid or bins >= 3)
+        if enough or len(wins) >= 2000 or time.perf_counter() - t_start > budget_s:
+            break
+    return wins, dict(dev_s=tot_s, steps=tot_steps, binnings=int(bins), sort_ms=sort_ms, infl_ms=infl_ms,
+                      steps_seen=seen, replayed=int(replay))
+
+
 def run_ours(args, w, rank, world, local_rank):
     from ctypes import byref, c_uint64 as C_uint64
 
@@ -318,15 +406,23 @@ def run_ours(args, w, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(*vals):
+        if dist is None:
+            return vals
+        tt = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tuple(float(x) for x in tt)
+
     method = {"grid": _lib.METHOD_GRID, "allpairs": _lib.METHOD_ALLPAIRS,
               "small": _lib.METHOD_SMALL}[w["method_resolved"]]
     t = w["tables"]
+    numerics = {None: None, "exact": _lib.NUMERICS_EXACT, "fast": _lib.NUMERICS_FAST}[args.numerics]
     kw = dict(
         bounding_box=(BoundingBox(t["bbox"][0:2], t["bbox"][2:4], t["bbox"][4:6]) if "bbox" in t else None),
         lead_boids=make_leads(w),
         obstacles=[Obstacle(o[:3], float(o[3])) for o in t["obstacles"]] if "obstacles" in t else None,
         attractors=[PointAttractor(a[:3], float(a[3])) for a in t["attractors"]] if "attractors" in t else None,
-        method=method, device=local_rank)
+        method=method, device=local_rank, numerics=numerics)
     n = w["n"]
     if world == 1:
         sim = Simulation.from_state(w["state"], **kw)
@@ -334,6 +430,8 @@ def run_ours(args, w, rank, world, local_rank):
         from feriphys_b200.sharded import ShardedSimulation
         sim = ShardedSimulation.from_global_slice(w["state"], n, w["first"], dist, **kw)
     sim.set_config(py_config(w["cfg"]))
+    numerics_in_use = "fast" if sim.numerics()[1] == _lib.NUMERICS_FAST else "exact"
+    grid = w["method_resolved"] == "grid"
 
     K, W = args.steps, args.warmup
     lib = _lib.load()
@@ -341,24 +439,12 @@ def run_ours(args, w, rank, world, local_rank):
     sim.sync()
     census = sim.pair_census()          # outside the timed region (extra launches)
     sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    rb0 = sim.rebin_info()
+    sampler.start()                     # (before the barrier: the Popen must not sit inside a window)
     launches0 = lib.fp_launch_count()
-    sim.timing_begin()
-    t0 = time.perf_counter()
-    sim.step_many(K)
-    barrier()
-    wall = time.perf_counter() - t0
-    nst, span_ms, sort_ms, infl_ms = sim.timing_end()
+    wins, tot = timed_windows(sim, K, barrier, reduce_max, grid)
     launches = lib.fp_launch_count() - launches0
-    rb1 = sim.rebin_info()
-    clocks = None
-    dev_s = span_ms / 1e3
+    dev_s = tot["dev_s"]
     if dist is not None:
-        tt = torch.tensor([dev_s, wall], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_s, wall = float(tt[0]), float(tt[1])
         ll = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(ll)
         launches = int(ll[0])
@@ -372,154 +458,189 @@ def run_ours(args, w, rank, world, local_rank):
         if int(chk[0]) != n or int(chk[1]):
             raise SystemExit(f"sharded run inconsistent: {int(chk[0])} boids owned of {n}, "
                              f"{int(chk[1])} ranks raised capacity/halo/barrier flags (this rank: {bad})")
-    if dev_s < 0.5:
-        # the timed region is shorter than a few nvidia-smi sampling periods: keep the same steps
-        # running (untimed, every rank alike) for ~1 s so that the clocks are read under this load
-        extra = int(min(20000, max(K, 1.0 / (dev_s / K))))
-        sim.step_many(extra)
-        sim.sync()
-        clocks = sampler.stop()
-        clocks["note"] = f"sampled over the timed steps and an untimed continuation of {extra} more"
-    else:
-        clocks = sampler.stop()
-    value = n * K / dev_s
+    clocks = sampler.stop()
+    steps_timed = tot["steps"]
+    value = n * steps_timed / dev_s
+    ms_per_step = 1e3 * dev_s / steps_timed
 
-    # ---- e2e: the drop-in call sequence with HOST buffers, copies inside the timed region
+    # ---- e2e: the drop-in call sequence with HOST buffers, copies inside the timed region.  Every rank
+    # uploads the rows it holds from pinned memory, steps once, reads them back -- the same at every N.
     e2e = None
-    if not args.no_e2e and world == 1:
-        host_in = torch.from_numpy(np.ascontiguousarray(w["state"])).pin_memory()
-        host_out = torch.empty_like(host_in).pin_memory()
-        a_in, a_out = host_in.numpy(), host_out.numpy()
+    if not args.no_e2e:
         ke = max(1, min(K, 10))
-        sim.write_state(a_in); sim.step_many(1); a_out[:] = sim.read_state()   # warm
-        barrier()
-        te = time.perf_counter()
-        for _ in range(ke):
-            _lib.check(lib.fp_flock_write_state(sim._h, _lib.ptr(a_in)))     # H2D
-            sim.step_many(1)
-            _lib.check(lib.fp_flock_read_state(sim._h, _lib.ptr(a_out)))     # D2H (synchronises)
-        barrier()
-        te = time.perf_counter() - te
-        e2e = {"value": n * ke / te, "unit": "boid-steps/s", "h2d_bytes_per_step": int(n * 24),
-               "d2h_bytes_per_step": int(n * 24), "steps": ke,
-               "path": "fp_flock_write_state -> fp_flock_step -> fp_flock_read_state, pinned host buffers"}
-        # the reference's own per-frame call sequence (demos/flocking.rs:215-227): step(), then
-        # get_boid_instances(); the state stays where Simulation keeps it
-        inst = torch.empty((n, 8), dtype=torch.float32).pin_memory().numpy()
-        _lib.check(lib.fp_flock_read_instances(sim._h, _lib.ptr(inst)))
-        barrier()
-        tf = time.perf_counter()
-        for _ in range(ke):
-            sim.step()
+        if world == 1:
+            host_in = torch.from_numpy(np.ascontiguousarray(w["state"])).pin_memory()
+            host_out = torch.empty_like(host_in).pin_memory()
+            a_in, a_out = host_in.numpy(), host_out.numpy()
+            sim.write_state(a_in); sim.step_many(1); a_out[:] = sim.read_state()   # warm
+            barrier()
+            te = time.perf_counter()
+            for _ in range(ke):
+                _lib.check(lib.fp_flock_write_state(sim._h, _lib.ptr(a_in)))     # H2D
+                sim.step_many(1)
+                _lib.check(lib.fp_flock_read_state(sim._h, _lib.ptr(a_out)))     # D2H (synchronises)
+            barrier()
+            te = time.perf_counter() - te
+            e2e = {"value": n * ke / te, "unit": "boid-steps/s", "h2d_bytes_per_step": int(n * 24),
+                   "d2h_bytes_per_step": int(n * 24), "steps": ke,
+                   "path": "fp_flock_write_state -> fp_flock_step -> fp_flock_read_state, pinned host buffers"}
+            # the reference's own per-frame call sequence (demos/flocking.rs:215-227): step(), then
+            # get_boid_instances(); the state stays where Simulation keeps it
+            inst = torch.empty((n, 8), dtype=torch.float32).pin_memory().numpy()
             _lib.check(lib.fp_flock_read_instances(sim._h, _lib.ptr(inst)))
-        barrier()
-        tf = time.perf_counter() - tf
-        e2e["frame"] = {"value": n * ke / tf, "unit": "boid-steps/s", "d2h_bytes_per_step": int(n * 32),
-                        "h2d_bytes_per_step": int(28 * len(sim.lead_boids or [])),
-                        "path": "Simulation.step() -> get_boid_instances() each step (lead rows up, instances down)"}
-    elif not args.no_e2e:
-        # sharded: every rank steps and reads back the boids it owns
-        cap_l = int(min(n, 2 * (n // world) + (1 << 20)))       # slabs are never this unbalanced here
-        idx_l = torch.empty(cap_l, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
-        st_l = torch.empty((cap_l, 6), dtype=torch.float32).pin_memory().numpy()
-        sim.step_many(1)
-        assert len(sim.read_local()[0]) <= cap_l
-        ke = max(1, min(K, 10))
-        barrier()
-        te = time.perf_counter()
-        for _ in range(ke):
+            barrier()
+            tf = time.perf_counter()
+            for _ in range(ke):
+                sim.step()
+                _lib.check(lib.fp_flock_read_instances(sim._h, _lib.ptr(inst)))
+            barrier()
+            tf = time.perf_counter() - tf
+            e2e["frame"] = {"value": n * ke / tf, "unit": "boid-steps/s", "d2h_bytes_per_step": int(n * 32),
+                            "h2d_bytes_per_step": int(28 * len(sim.lead_boids or [])),
+                            "path": "Simulation.step() -> get_boid_instances() each step (lead rows up, instances down)"}
+        else:
+            cap_l = int(min(n, 2 * (n // world) + (1 << 20)))       # slabs are never this unbalanced here
+            idx_l = torch.empty(cap_l, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+            st_l = torch.empty((cap_l, 6), dtype=torch.float32).pin_memory().numpy()
+            own = C_uint64()
+
+            def rows():
+                _lib.check(lib.fp_flock_local_len(sim._h, byref(own)))
+                assert own.value <= cap_l
+                return int(own.value)
+
             sim.step_many(1)
-            _lib.check(lib.fp_flock_read_local(sim._h, _lib.ptr(idx_l), _lib.ptr(st_l)))
-        barrier()
-        te = time.perf_counter() - te
-        tt = torch.tensor([te], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * ke / float(tt[0]), "unit": "boid-steps/s", "h2d_bytes_per_step": 0,
-               "d2h_bytes_per_step": int(n * 32), "steps": ke,
-               "path": "fp_flock_step -> fp_flock_read_local on every rank (each rank reads the boids it owns)"}
+            m = rows()
+            _lib.check(lib.fp_flock_read_local(sim._h, _lib.ptr(idx_l), _lib.ptr(st_l)))    # warm
+            h2d = d2h = 0
+            barrier()
+            te = time.perf_counter()
+            for _ in range(ke):
+                _lib.check(lib.fp_flock_write_local(sim._h, m, _lib.ptr(idx_l), _lib.ptr(st_l)))   # H2D
+                sim.step_many(1)
+                h2d += m * 32
+                m = rows()                                                                    # (boids migrate)
+                _lib.check(lib.fp_flock_read_local(sim._h, _lib.ptr(idx_l), _lib.ptr(st_l)))   # D2H
+                d2h += m * 32
+            barrier()
+            te = time.perf_counter() - te
+            tt = torch.tensor([te], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            bb = torch.tensor([h2d, d2h], device="cuda", dtype=torch.int64)
+            dist.all_reduce(bb)
+            e2e = {"value": n * ke / float(tt[0]), "unit": "boid-steps/s",
+                   "h2d_bytes_per_step": int(bb[0]) // ke, "d2h_bytes_per_step": int(bb[1]) // ke, "steps": ke,
+                   "path": "every rank: fp_flock_write_local (the rows it holds, pinned) -> fp_flock_step -> "
+                           "fp_flock_read_local; bytes summed over ranks"}
+
+    # ---- the other arithmetic, for comparison (same flock, same harness, shorter)
+    other = None
+    if not args.no_alt and w["method_resolved"] != "small":
+        alt = _lib.NUMERICS_EXACT if numerics_in_use == "fast" else _lib.NUMERICS_FAST
+        sim.set_numerics(alt)
+        if (sim.numerics()[1] == _lib.NUMERICS_FAST) != (numerics_in_use == "fast"):
+            sim.step_many(max(3, W))
+            sim.sync()
+            awins, atot = timed_windows(sim, K, barrier, reduce_max, grid, budget_s=8.0)
+            other = {"numerics": "exact" if alt == _lib.NUMERICS_EXACT else "fast",
+                     "ms_per_step": 1e3 * atot["dev_s"] / atot["steps"], "value": n * atot["steps"] / atot["dev_s"],
+                     "influence_ms_per_step": atot["infl_ms"] / atot["steps_seen"], "steps": atot["steps"],
+                     "binnings": atot["binnings"]}
+        sim.set_numerics(_lib.NUMERICS_FAST if numerics_in_use == "fast" else _lib.NUMERICS_EXACT)
+
+    parity = None if args.no_parity else parity_check(sim, w, rank)
 
     hbm, sm_max, peak_src = measured_peaks()
-    steps_seen = max(1, nst)
-    grid = w["method_resolved"] == "grid"
+    steps_seen = max(1, tot["steps_seen"])
     in_range, candidates = pairs_per_boid_step(census, n)
     # (on a sharded flock fp_flock_pair_census already returns the all-rank totals)
     flops_step = 8.0 * float(census[0]) + 18.0 * float(census[1]) + 54.0 * float(census[2])
-    infl_s = infl_ms / 1e3 / steps_seen if w["method_resolved"] != "small" else dev_s / K
+    infl_s = tot["infl_ms"] / 1e3 / steps_seen if w["method_resolved"] != "small" else dev_s / steps_timed
     n_local = n / world
+    fma_peak = FP32_LANES * 2 * sm_max * 1e6 / 1e12
+    fast = numerics_in_use == "fast"
+    # The binder of every influence kernel here is FP32 instruction issue, not HBM and not the tensor
+    # cores (the path is no contraction).  EXACT numerics forbid FMA contraction: their cap is the
+    # non-FMA issue peak, half of the FMA peak FAST numerics are measured against.
+    peak = fma_peak if fast else fma_peak / 2
+    roofline = {"bound": "fp32_issue", "achieved": flops_step / world / infl_s / 1e12, "peak": peak, "unit": "TFLOP/s",
+                "flops_per_step": flops_step,
+                "peak_source": f"148 SM x 128 FP32 lanes x clocks.max.sm ({sm_max:.0f} MHz): "
+                               + ("x 2 (FMA peak)" if fast else "x 1 (exact arithmetic cannot fuse: non-FMA issue peak)"),
+                "model": "8 / 18 / 54 flops per examined pair by outcome (SURVEY 8d.1), pairs counted once on the "
+                         "post-warm-up state, over the influence kernel's CUDA-event time",
+                "traffic": None}
+    roofline["frac"] = roofline["achieved"] / roofline["peak"]
     if grid:
+        lists = os.environ.get("FP_NL", "1") != "0"
+        roofline["kernel"] = (("nl_fast_kernel" if fast else "nl_walk_kernel") + " (walk on standing candidate lists"
+                              " + extras + Euler)") if lists else "grid_walk3_kernel<TAP_STEP> (TMA-staged 27-cell walk)"
         traffic, traffic_src = None, None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch (profiles/)
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
-                t = json.load(fh).get(w["name"])
-            if t and t["boids"] == n and world == 1:
-                traffic = t["dram_bytes_per_launch"]      # bytes per launch (algorithmic: 64 * n)
-                traffic_src = t["source"]
+                tr = json.load(fh).get(f"{w['name']}_{numerics_in_use}" if lists else w["name"])
+            if tr and tr["boids"] == n and world == 1:
+                traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
         except Exception:
             pass
-        variant = os.environ.get("FP_WALK_VARIANT", "")
-        lists = variant in ("41", "43", "44", "45", "46") and world == 1 or variant == "42"
-        if lists:   # experimental candidate-list walk: no ncu capture of it yet
-            traffic, traffic_src = None, None
-        roofline = {"bound": "hbm", "kernel": (f"nl_walk_kernel (FP_WALK_VARIANT={variant}: walk on standing candidate lists)"
-                                               if lists else
-                                               "grid_walk3_kernel<TAP_STEP> (TMA-staged 27-cell walk + extras + Euler)"),
-                    "achieved": 64.0 * n_local / infl_s / 1e9, "peak": hbm, "unit": "GB/s",
-                    "algorithmic_bytes_per_boid": 64, "traffic": traffic, "traffic_source": traffic_src,
-                    "algorithmic_bytes_per_launch": 64 * int(n_local), "peak_source": peak_src,
-                    "note": "SURVEY 8d.2 floor of 64 B/boid (state read + write); by design the kernel also "
-                            "reads the 4 B home key and writes the 12 B SoA copy (80 B/boid).  FP32-issue "
-                            "bound, not HBM bound (ncu: DRAM 3 % busy, issue slots 73 %); the north star names "
-                            "the HBM roofline, so the fraction is reported against it"}
+        roofline["traffic"] = traffic
+        roofline["traffic_source"] = traffic_src
+        # the HBM figure the north star names, beside the real binder
+        roofline["hbm"] = {"achieved": 64.0 * n_local / infl_s / 1e9, "peak": hbm, "unit": "GB/s",
+                           "frac": 64.0 * n_local / infl_s / 1e9 / hbm, "algorithmic_bytes_per_boid": 64,
+                           "algorithmic_bytes_per_launch": 64 * int(n_local), "peak_source": peak_src,
+                           "note": "SURVEY 8d.2 floor of 64 B/boid (state read + write) over the walk's time; the "
+                                   "walk also streams its candidate lists (~90 B/boid) and the SoA copy (12 B)"}
     else:
-        peak = FP32_LANES * 2 * sm_max * 1e6 / 1e12
-        roofline = {"bound": "fp32", "kernel": "allpairs2_kernel / allpairs_kernel<TAP_STEP> (the faster of the "
-                    "two, measured by the handle)" if w["method_resolved"] == "allpairs" else "small_kernel", "achieved": flops_step / world / infl_s / 1e12, "peak": peak,
-                    "unit": "TFLOP/s", "traffic": None,
-                    "peak_source": "148 SM x 128 lanes x 2 x clocks.max.sm (FMA peak; exact non-fused "
-                                   "arithmetic can reach at most half)"}
-    roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        roofline["kernel"] = ("allpairs_fast_kernel (j split across lanes, warp-shuffle reduction)" if fast else
+                              "allpairs2_kernel / allpairs_kernel<TAP_STEP> (the faster of the two, measured by the "
+                              "handle)") if w["method_resolved"] == "allpairs" else "small_kernel"
     line = {
         "metric": "boid-steps/sec", "value": value, "unit": "boid-steps/s", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True,
+        "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (splitmix64-keyed uniform flock, seed 0xFE21F)",
-        "config": config_block(w, args, world),
-        "pair_interactions_per_sec": in_range * K / dev_s,
-        "candidate_pairs_per_sec": candidates * K / dev_s,
+        "config": dict(config_block(w, args, world), numerics=numerics_in_use + (
+            " (neighbour sets bit-exact; forces fused, accelerations within 1e-5 of the reference)" if fast else
+            " (every operation separately rounded in the reference's order)")),
+        "pair_interactions_per_sec": in_range * steps_timed / dev_s,
+        "candidate_pairs_per_sec": candidates * steps_timed / dev_s,
         "pairs": {"rejected_by_distance": float(census[0]), "fov_culled": float(census[1]),
                   "contributing": float(census[2]), "examined": float(census[3]),
                   "note": "ordered pairs per step, counted once on the post-warm-up state"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "timing": {"device_span_ms": span_ms, "wall_ms": wall * 1e3, "sort_phase_ms_per_step": sort_ms / steps_seen,
-                   "influence_ms_per_step": infl_ms / steps_seen,
-                   "how": "CUDA events on the library's stream, max over ranks"},
-        "roofline": roofline,
+        "timing": {"windows": len(wins), "steps_timed": steps_timed, "device_s_timed": dev_s,
+                   "window_ms_per_step": {"median": float(np.median([x["ms_per_step"] for x in wins])),
+                                          "min": min(x["ms_per_step"] for x in wins),
+                                          "max": max(x["ms_per_step"] for x in wins)},
+                   "windows_head": wins[:12],
+                   "sort_phase_ms_per_step": tot["sort_ms"] / steps_seen,
+                   "influence_ms_per_step": tot["infl_ms"] / steps_seen,
+                   "how": f"windows of {K} steps, each bracketed by a barrier and timed with CUDA events on the "
+                          "library's stream, max over ranks; repeated until >= 1 s of device time and (grid) >= 3 "
+                          "binnings were inside; value and ms_per_step are totals over all windows, so every "
+                          "binning is paid for; sort_phase is amortised over the binnings observed"},
+        "roofline": roofline, "other_numerics": other, "parity": parity,
     }
-    if grid and rb0 is not None:
-        line["rebinning"] = {"skin": rb1[0], "binnings_in_timed_steps": rb1[2] - rb0[2],
-                             "steps_replayed": rb1[3] - rb0[3],
+    if grid:
+        rbi = sim.rebin_info()
+        line["rebinning"] = {"skin": rbi[0], "binnings_in_timed_steps": tot["binnings"],
+                             "steps_per_binning": steps_timed / max(1, tot["binnings"]),
+                             "steps_replayed": tot["replayed"],
                              "halo": (("peer stores fused into the walk kernel (cudaIpc over NVLink), mailbox "
                                        "step barrier" if sim.shard_info()[2] else "ncclSend/ncclRecv after each walk")
                                       if world > 1 else None),
-                             "note": "lazy re-binning: one sort by cell serves every step until some boid "
-                                     "could have moved skin/2 (device-checked); the timed steps include "
-                                     "their share of binnings"}
-    if grid:
-        step_s = dev_s / K
+                             "note": "lazy re-binning: one sort by cell (+ candidate-list build) serves every step "
+                                     "until some boid could have moved skin/2 (device-checked)"}
+        step_s = dev_s / steps_timed
         # 64 (walk) + 68 (gather) + 16 * 3 (sort passes) + 16 (keys) = 196 B per boid and
         # binning; with lazy re-binning only the walk's 64 B recur every step
-        bins = (rb1[2] - rb0[2]) if rb0 is not None else K
-        bytes_step = 64.0 + 132.0 * bins / K
+        bytes_step = 64.0 + 132.0 * tot["binnings"] / steps_timed
         line["roofline_step"] = {"bound": "hbm", "achieved": bytes_step * n_local / step_s / 1e9, "peak": hbm,
                                  "unit": "GB/s", "frac": bytes_step * n_local / step_s / 1e9 / hbm,
                                  "algorithmic_bytes_per_boid_step": bytes_step,
                                  "note": "whole step, SURVEY 8d.2 byte model: 64 B per step + 132 B (keys, sort, "
                                          "gather) per binning x binnings per step in the timed region"}
-        peak = FP32_LANES * 2 * sm_max * 1e6 / 1e12
-        line["fp32_model"] = {"flops_per_step": flops_step, "achieved": flops_step / world / infl_s / 1e12,
-                              "peak": peak, "unit": "TFLOP/s", "frac": flops_step / world / infl_s / 1e12 / peak,
-                              "note": "8/18/54 flops per examined pair by outcome (SURVEY 8d.1) over the "
-                                      "walk kernel's time; exact unfused arithmetic caps at frac 0.5"}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         r = OracleRunner(w, threads)

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libferiphys_cuda.so")
 
 OK = 0
 METHOD_AUTO, METHOD_ALLPAIRS, METHOD_GRID, METHOD_SMALL = 0, 1, 2, 3
+NUMERICS_EXACT, NUMERICS_FAST = 0, 1
 STATUS_STEER_NEGATIVE, STATUS_STEER_NAN_OVF = 1, 2
 
 
@@ -50,6 +51,8 @@ _PROTOS = {
     "fp_flock_get_config": (C.c_int, [_P, C.POINTER(FpConfig)]),
     "fp_flock_set_method": (C.c_int, [_P, C.c_int]),
     "fp_flock_get_method": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "fp_flock_set_numerics": (C.c_int, [_P, C.c_int]),
+    "fp_flock_get_numerics": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fp_flock_set_leads": (C.c_int, [_P, C.c_uint32, _P]),
     "fp_flock_set_attractors": (C.c_int, [_P, C.c_uint32, _P]),
     "fp_flock_set_obstacles": (C.c_int, [_P, C.c_uint32, _P]),
@@ -63,6 +66,7 @@ _PROTOS = {
     "fp_flock_status": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "fp_flock_read_instances": (C.c_int, [_P, _P]),
     "fp_flock_read_instances_raw": (C.c_int, [_P, _P]),
+    "fp_flock_export_instances": (C.c_int, [_P, _P, C.c_int]),
     "fp_flock_read_accel": (C.c_int, [_P, _P, _P]),
     "fp_flock_read_neighbors": (C.c_int, [_P, _P, _P]),
     "fp_flock_pair_census": (C.c_int, [_P, _P]),
@@ -85,6 +89,7 @@ _PROTOS = {
                                           C.c_uint64, _P, C.c_int, C.c_int, C.c_int, _P]),
     "fp_flock_local_len": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "fp_flock_read_local": (C.c_int, [_P, _P, _P]),
+    "fp_flock_write_local": (C.c_int, [_P, C.c_uint64, _P, _P]),
     "fp_debug_fastmath_check": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, _P]),
     "fp_last_error": (C.c_char_p, []),
     "fp_version": (C.c_char_p, []),

@@ -283,6 +283,213 @@ allpairs2_kernel(const DevParams P, const float4 *__restrict__ pos_all,
     if (flags) atomicOr(status, flags);
 }
 
+// ---- FAST numerics: j split across lanes, algebraic pre-gate, fused forces -------------------------
+// A thread owns TWO boids (A, B) and one of JS interleaved slices of the candidates; the JS partial
+// sums of a boid are combined with warp shuffles at the end (JS lanes of one warp), so a 100k-boid
+// flock still fills the machine (C2: 64 rows per CTA, 1563 CTAs).  Per batch of four candidates:
+//   pre-gate  -- |p_j - p_i|^2 = |p_j|^2 - 2 p_i . p_j + |p_i|^2 with |p_j|^2 staged per candidate and
+//                |p_i|^2 folded into the threshold: three FMAs per pair (two pairs per FFMA2) instead
+//                of three subtractions and three multiply-adds.  Coordinates are taken relative to
+//                the flock's centre and the cancellation error (<= 1.2e-6 M^2, M the largest centred
+//                norm) is added to the cut, so the survivors are a superset of the pairs in range;
+//   survivors -- the reference's own squared distance (separately rounded) decides "in range" and
+//                "weight 1"; the sight-angle decision and the forces are those of the fast grid walk
+//                (fp_walk_nl.cu): fused cosine outside a 1e-5 guard band, exact sequence inside it.
+// Neighbour sets are bit-exact; accelerations differ from the reference by rounding and summation
+// order (~1e-6 relative).
+constexpr int APF_TJ = 256;  // candidates per tile
+
+struct ApfSmem {
+    alignas(16) float xc[APF_TJ], yc[APF_TJ], zc[APF_TJ], w[APF_TJ];  // centred position, |.|^2
+    float4 tp[APF_TJ], tv[APF_TJ];                                    // the records themselves
+};
+
+struct ApfBoid {
+    Self self;
+    float2 ax2, ay2, az2;  // -2 (p - centre), both halves
+    float thr;             // cut + margin - |p - centre|^2
+    float ax, ay, az;      // partial acceleration
+};
+
+__device__ __forceinline__ void apf_pair(const DevParams &P, ApfBoid &b, const float4 pj, const float4 *tvj,
+                                         bool live) {
+    // (the fast grid walk's pair, fp_walk_nl.cu: fast_gate + fast_force)
+    const Self &self = b.self;
+    const float dx = fsub(pj.x, self.p.x), dy = fsub(pj.y, self.p.y), dz = fsub(pj.z, self.p.z);
+    const float m2 = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+    const float q = fmaf(self.vhat.z, dz, fmaf(self.vhat.y, dy, self.vhat.x * dx));
+    const float r = rsqrt_seed(m2);
+    const float c = q * r;
+    const float gc = (c - P.fz_a) * (c - P.fz_b);
+    const bool in = live && !(m2 >= P.m2_cut);
+    const bool clear = fabsf(gc) > P.fz_gc_tol && m2 >= 1e-12f;
+    if (in && clear && gc > 0.0f) {
+        const float4 vj = *tvj;
+        const float g0 = m2 * r, h = 0.5f * r;
+        const float mag = fmaf(fmaf(-g0, g0, m2), h, g0);
+        const float coef = fmaf(P.f_c, mag, P.neg_f_a * (r * r)) * r;
+        const float w = m2 <= P.m2_one ? 1.0f : (mag - P.thr) * P.fz_rinv_fall;
+        const float dvx = vj.x - self.v.x, dvy = vj.y - self.v.y, dvz = vj.z - self.v.z;
+        const bool vsm = fmaxf(fmaxf(fabsf(dvx), fabsf(dvy)), fabsf(dvz)) <= FP_F32_EPSILON;
+        const float cw = coef * w, fw = vsm ? 0.0f : P.f_v * w;
+        b.ax = fmaf(cw, dx, fmaf(fw, dvx, b.ax));
+        b.ay = fmaf(cw, dy, fmaf(fw, dvy, b.ay));
+        b.az = fmaf(cw, dz, fmaf(fw, dvz, b.az));
+    } else if (in && !clear) {
+        // guard band / coincident / NaN (rare; the boid's own record lands here once): exact sequence.
+        // The reference skips records equal to the boid (flocking.rs:137-139); their exact
+        // contribution is +0 for finite states, so evaluating them changes nothing.
+        const float4 vj = *tvj;
+        V3 contrib;
+        if (pair_inrange<false>(P, self, v3(dx, dy, dz), m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar, contrib)) {
+            b.ax += contrib.x;
+            b.ay += contrib.y;
+            b.az += contrib.z;
+        }
+    }
+}
+
+template <int TAP>
+__global__ void __launch_bounds__(AP_BLOCK, 4)
+allpairs_fast_kernel(const DevParams P, const float4 *__restrict__ pos_all, const float4 *__restrict__ vel_all,
+                     uint32_t n_all, uint32_t row0, uint32_t nrows, int js_log2, const float *__restrict__ bounds8,
+                     float4 *__restrict__ pos_out, float4 *__restrict__ vel_out, unsigned *__restrict__ status,
+                     TapOut tap) {
+    __shared__ ApfSmem S;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t JS = 1u << js_log2, slice = tid & (JS - 1u), rowslot = tid >> js_log2;
+    const uint32_t rows_per_cta = 2u * (AP_BLOCK >> js_log2);
+    // centre of the flock and the cancellation margin of the pre-gate (bounds_kernel: finite positions)
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f, margin = INFINITY;
+    {
+        const float lx = __ldg(bounds8 + 0), ly = __ldg(bounds8 + 1), lz = __ldg(bounds8 + 2);
+        const float hx = __ldg(bounds8 + 3), hy = __ldg(bounds8 + 4), hz = __ldg(bounds8 + 5);
+        if (lx <= hx && ly <= hy && lz <= hz) {
+            cx = 0.5f * (lx + hx); cy = 0.5f * (ly + hy); cz = 0.5f * (lz + hz);
+            const float ex = fmaxf(hx - cx, cx - lx), ey = fmaxf(hy - cy, cy - ly), ez = fmaxf(hz - cz, cz - lz);
+            const float M2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex)) * 1.0001f + 1e-30f;
+            margin = 2.5e-6f * M2;  // twice the bound on |t - (|p_j|^2 - 2 p_i . p_j)| + the threshold's rounding
+        }
+        if (!(cx == cx && cy == cy && cz == cz) || fabsf(cx) == INFINITY || fabsf(cy) == INFINITY || fabsf(cz) == INFINITY) {
+            cx = cy = cz = 0.0f;
+            margin = INFINITY;  // (everything survives the pre-gate: still correct)
+        }
+    }
+    ApfBoid b[2];
+    float4 pi4[2], vi4[2];
+    bool act[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t r = blockIdx.x * rows_per_cta + 2u * rowslot + k;
+        act[k] = r < nrows;
+        const uint32_t i = row0 + (act[k] ? r : 0u);
+        pi4[k] = __ldg(pos_all + i);
+        vi4[k] = __ldg(vel_all + i);
+        b[k].self = make_self(v3(pi4[k].x, pi4[k].y, pi4[k].z), v3(vi4[k].x, vi4[k].y, vi4[k].z));
+        const float px = pi4[k].x - cx, py = pi4[k].y - cy, pz = pi4[k].z - cz;
+        b[k].ax2 = make_float2(-2.0f * px, -2.0f * px);
+        b[k].ay2 = make_float2(-2.0f * py, -2.0f * py);
+        b[k].az2 = make_float2(-2.0f * pz, -2.0f * pz);
+        b[k].thr = (P.m2_cut + margin) - fmaf(pz, pz, fmaf(py, py, px * px));
+        b[k].ax = b[k].ay = b[k].az = 0.0f;
+    }
+    const bool need_pairs = (TAP != TAP_STEP) || !P.steering_overrides;
+    if (need_pairs) {
+        for (uint32_t j0 = 0; j0 < n_all; j0 += APF_TJ) {
+            __syncthreads();  // everyone is done with the previous tile
+#pragma unroll
+            for (int h = 0; h < APF_TJ / AP_BLOCK; ++h) {
+                const uint32_t t = tid + h * AP_BLOCK, jl = j0 + t;
+                float4 pj = make_float4(1e18f, 1e18f, 1e18f, 0.0f), vj = make_float4(0, 0, 0, 0);  // padding: far, finite
+                if (jl < n_all) {
+                    pj = __ldg(pos_all + jl);
+                    vj = __ldg(vel_all + jl);
+                }
+                const float x = pj.x - cx, y = pj.y - cy, z = pj.z - cz;
+                S.xc[t] = x; S.yc[t] = y; S.zc[t] = z;
+                S.w[t] = fmaf(z, z, fmaf(y, y, x * x));
+                S.tp[t] = pj;
+                S.tv[t] = vj;
+            }
+            __syncthreads();
+            const uint32_t cnt = min((uint32_t)APF_TJ, n_all - j0);
+            for (uint32_t q = slice; 4u * q < cnt; q += JS) {
+                const float4 X = *reinterpret_cast<const float4 *>(&S.xc[4 * q]);
+                const float4 Y = *reinterpret_cast<const float4 *>(&S.yc[4 * q]);
+                const float4 Z = *reinterpret_cast<const float4 *>(&S.zc[4 * q]);
+                const float4 W = *reinterpret_cast<const float4 *>(&S.w[4 * q]);
+                const float2 X01 = make_float2(X.x, X.y), X23 = make_float2(X.z, X.w);
+                const float2 Y01 = make_float2(Y.x, Y.y), Y23 = make_float2(Y.z, Y.w);
+                const float2 Z01 = make_float2(Z.x, Z.y), Z23 = make_float2(Z.z, Z.w);
+                const float2 W01 = make_float2(W.x, W.y), W23 = make_float2(W.z, W.w);
+                bool hit = false;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float2 t01 = __ffma2_rn(b[k].ax2, X01, __ffma2_rn(b[k].ay2, Y01, __ffma2_rn(b[k].az2, Z01, W01)));
+                    const float2 t23 = __ffma2_rn(b[k].ax2, X23, __ffma2_rn(b[k].ay2, Y23, __ffma2_rn(b[k].az2, Z23, W23)));
+                    // one compare per boid and batch.  (fminf drops a NaN operand: a record with a
+                    // non-finite position can go unseen here -- FAST numerics are defined on finite states.)
+                    hit |= !(fminf(fminf(t01.x, t01.y), fminf(t23.x, t23.y)) >= b[k].thr);
+                }
+                if (hit) {  // someone may be in range: the whole batch takes the exact distance test
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t t = 4 * q + u;
+                        const float4 pj = S.tp[t];
+                        apf_pair(P, b[0], pj, &S.tv[t], t < cnt);
+                        apf_pair(P, b[1], pj, &S.tv[t], t < cnt);
+                    }
+                }
+            }
+        }
+    }
+    // the JS partial sums of each boid -> its slice-0 lane
+    for (uint32_t off = JS >> 1; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            b[k].ax += __shfl_xor_sync(0xffffffffu, b[k].ax, off);
+            b[k].ay += __shfl_xor_sync(0xffffffffu, b[k].ay, off);
+            b[k].az += __shfl_xor_sync(0xffffffffu, b[k].az, off);
+        }
+    }
+    if (slice != 0) return;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (!act[k]) continue;
+        const uint32_t r = blockIdx.x * rows_per_cta + 2u * rowslot + k;
+        const uint32_t idx = __float_as_uint(pi4[k].w);  // caller index
+        const V3 acc = v3(b[k].ax, b[k].ay, b[k].az);
+        Extras e;
+        unsigned flags = 0;
+        const V3 a = accel_total_fast(P, b[k].self, acc, e, flags, TAP == TAP_ACCEL);
+        if (TAP == TAP_ACCEL) {
+            float *o = tap.accel3 + 3ull * idx;
+            o[0] = a.x; o[1] = a.y; o[2] = a.z;
+            if (tap.comp15) {
+                float *c = tap.comp15 + 15ull * idx;
+                c[0] = acc.x; c[1] = acc.y; c[2] = acc.z;
+                c[3] = e.lead.x; c[4] = e.lead.y; c[5] = e.lead.z;
+                c[6] = e.attr.x; c[7] = e.attr.y; c[8] = e.attr.z;
+                c[9] = e.bbox.x; c[10] = e.bbox.y; c[11] = e.bbox.z;
+                c[12] = e.steer.x; c[13] = e.steer.y; c[14] = e.steer.z;
+            }
+        } else {
+            V3 np, nv;
+            euler(P, b[k].self.p, b[k].self.v, a, np, nv);
+            pos_out[r] = make_float4(np.x, np.y, np.z, pi4[k].w);
+            vel_out[r] = make_float4(nv.x, nv.y, nv.z, 0.0f);
+        }
+        if (flags) atomicOr(status, flags);
+    }
+}
+
+// rows a CTA of the fast kernel covers, and the j-split that fills the machine
+static int apf_js_log2(uint32_t nrows) {
+    int js = 0;  // 256 rows per CTA when the flock is large
+    while (js < 5 && (uint64_t)nrows * (1u << js) < 256ull * 148 * 8) ++js;
+    return js;
+}
+
 template <int TAP>
 static int launch_ap2(cudaStream_t st, const dim3 grid, const DevParams &P, const float4 *pos_all,
                       const float4 *vel_all, uint32_t n_all, uint32_t row0, uint32_t nrows, float4 *pos_out,
@@ -296,8 +503,23 @@ static int launch_ap2(cudaStream_t st, const dim3 grid, const DevParams &P, cons
 
 int launch_allpairs(cudaStream_t st, const DevParams &P, int tap, const float4 *pos_all,
                     const float4 *vel_all, uint32_t n_all, uint32_t row0, uint32_t nrows,
-                    float4 *pos_out, float4 *vel_out, unsigned *status, const TapOut &tap_out, int variant) {
+                    float4 *pos_out, float4 *vel_out, unsigned *status, const TapOut &tap_out, int variant,
+                    const float *bounds8) {
     if (nrows == 0) return FP_OK;
+    if (P.numerics_fast && bounds8 && (tap == TAP_STEP || tap == TAP_ACCEL)) {
+        const int js = apf_js_log2(nrows);
+        const uint32_t rows_per_cta = 2u * (AP_BLOCK >> js);
+        const dim3 gridf((nrows + rows_per_cta - 1) / rows_per_cta);
+        if (tap == TAP_STEP)
+            allpairs_fast_kernel<TAP_STEP><<<gridf, AP_BLOCK, 0, st>>>(P, pos_all, vel_all, n_all, row0, nrows, js, bounds8,
+                                                                     pos_out, vel_out, status, tap_out);
+        else
+            allpairs_fast_kernel<TAP_ACCEL><<<gridf, AP_BLOCK, 0, st>>>(P, pos_all, vel_all, n_all, row0, nrows, js, bounds8,
+                                                                      pos_out, vel_out, status, tap_out);
+        count_launch();
+        FP_CUDA(cudaGetLastError());
+        return FP_OK;
+    }
     const dim3 grid((nrows + AP_BLOCK - 1) / AP_BLOCK), block(AP_BLOCK);
     // variant 0: staged (pre-gate + lists; wins when most pairs are out of range), 1: one-phase
     // (wins in dense flocks where most candidates contribute).  Same bits either way; the

@@ -71,7 +71,7 @@ static float acos_threshold(float theta) {
     return unord(lo);
 }
 
-void derive_params(const fp_config &c, DevParams &P) {
+void derive_params(const fp_config &c, DevParams &P, bool want_fast) {
     P.dt = c.dt;
     P.f_c = c.centering_factor;
     P.f_v = c.velocity_matching_factor;
@@ -108,6 +108,24 @@ void derive_params(const fp_config &c, DevParams &P) {
     int e = 0;
     P.fall_pow2 = P.fast_ok && frexpf(P.fall, &e) == 0.5f;
     P.inv_fall = P.fall_pow2 ? 1.0f / P.fall : 0.0f;
+    // FAST numerics: usable when the thresholds are ordinary numbers (else the exact kernels run)
+    const bool fz_ok = P.fast_ok && std::isfinite(P.m2_cut) && P.m2_cut > 0.0f && P.m2_one < P.m2_cut &&
+                       P.cstar >= -2.0f && P.cstar <= 1.0f && P.cstar_lead >= -2.0f;
+    P.numerics_fast = want_fast && fz_ok;
+    P.fz_one = P.m2_one;
+    if (P.cstar < -1.0f) P.fz_a = P.fz_b = -3.0f;  // nothing is ever culled
+    else { P.fz_a = P.cstar; P.fz_b = -1.0f; }
+    // the fused cosine is within 1e-6 of the reference's; decisions within 1e-5 of either end of
+    // the culled interval are re-taken exactly: |(c - a)(c - b)| <= 1e-5 (|a - b| + 1e-5) covers them
+    P.fz_gc_tol = 1e-5f * (fabsf(P.fz_a - P.fz_b) + 1e-5f);
+    P.fz_gm_tol = 0.0f;  // (the fast walk computes the squared distance exactly: no band needed)
+    P.fz_rinv_fall = P.fall != 0.0f ? 1.0f / P.fall : 0.0f;
+    {
+        // obstacles farther than radius + |v| t_start (1 + 1e-4) cannot start steering: skipped.
+        // Safe against Duration's ns rounding when t_start 1e-4 >> 1 ns.
+        const double ts = (double)c.time_to_start_steering_secs + 1e-9 * (double)c.time_to_start_steering_nanos;
+        P.fz_steer_reach = (ts >= 1e-4 && ts < 1e30) ? (float)(ts * 1.0001) : -1.0f;
+    }
 }
 
 }  // namespace fp
@@ -131,7 +149,7 @@ void dev_free(T *&p) {
     p = nullptr;
 }
 
-// bookkeeping of the experimental candidate lists: the flock has just been binned
+// bookkeeping of the candidate lists: the flock has just been binned
 void nl_binned(fp_flock *f) {
     f->nl_fresh = true;
     f->nl_prev_bin_steps = f->nl_bin_steps;
@@ -149,6 +167,7 @@ int ensure_stage(fp_flock *f, size_t bytes) {
 }
 
 int settle(fp_flock *f);
+bool nl_enabled();  // candidate lists (below): FP_NL=0 turns them off
 
 // every entry point except fp_flock_step: the handle must be valid and every enqueued step
 // must be known to have happened (lazy re-binning may have voided some: settle replays them)
@@ -161,18 +180,23 @@ int check(fp_flock *f, bool settled = true) {
     return settled ? settle(f) : FP_OK;
 }
 
-int upload_table(fp_flock *f, float **dst, const float *src, size_t floats) {
-    dev_free(*dst);
-    if (!floats) return FP_OK;
-    int rc = dev_alloc(dst, floats);
-    if (rc) return rc;
+// (the allocation is kept when the new table fits it)
+int upload_table(fp_flock *f, float **dst, size_t *cap, const float *src, size_t floats) {
+    if (!floats) return FP_OK;  // (the count the kernels see is 0; the old table is never read)
+    if (!*dst || floats > *cap) {
+        dev_free(*dst);
+        *cap = 0;
+        int rc = dev_alloc(dst, floats);
+        if (rc) return rc;
+        *cap = floats;
+    }
     FP_CUDA(cudaMemcpyAsync(*dst, src, floats * sizeof(float), cudaMemcpyHostToDevice, f->stream));
     FP_CUDA(cudaStreamSynchronize(f->stream));  // caller's buffer is not retained
     return FP_OK;
 }
 
 void refresh_tables(fp_flock *f) {
-    f->P.leads = f->d_leads;
+    f->P.leads = f->n_leads ? f->d_lead_ring + (size_t)(f->lead_ver % fp_flock::LEAD_RING) * f->n_leads * 8 : nullptr;
     f->P.n_leads = (int)f->n_leads;
     f->P.attractors = f->d_attr;
     f->P.n_attractors = (int)f->n_attr;
@@ -247,13 +271,17 @@ int fit_grid(fp_flock *f) {
     // (DESIGN.md 4.1), delta = the per-step displacement bound.  Flocks too fast for two steps
     // per binning get none.
     const float delta = plan_delta(v2max, pmax, f->cfg.dt);
-    // cost ratio binning : step.  Both grow with the boids a GPU holds (0.15 measured at C4), but
-    // a binning also has a fixed part -- ~20 launches, and on a sharded flock four NCCL groups
-    // and three host syncs (0.5 ms fits the 8-GPU measurements: skin 0.11 / 0.25 / 0.42 gave
-    // 0.798 / 0.772 / 0.791 ms per step) -- that a small or sharded flock amortises over more
-    // steps with a larger skin.
+    // cost ratio binning : step.  Both grow with the boids a GPU holds, but a binning also has a
+    // fixed part -- ~20 launches, and on a sharded flock four NCCL groups and three host syncs
+    // (0.5 ms fitted the 8-GPU measurements of round 1) -- that a small or sharded flock
+    // amortises over more steps with a larger skin.
     const double n_here = std::max<double>(1.0, f->shard ? (double)f->n_global / shard_world(f->shard) : f->n);
-    const double ratio = 0.15 + (f->shard ? 0.5e-3 : 1.0e-4) / (n_here * 0.34e-9);
+    // per-boid costs measured at C4 (ns): a binning 0.06 and, with candidate lists, their build 0.23;
+    // a step 0.34 (staged walk), 0.20 (exact list walk) or 0.11 (fast list walk)
+    const bool lists = nl_enabled() && !f->nl_off;
+    const double c_bin = 0.06e-9 + (lists ? 0.23e-9 : 0.0);
+    const double c_step = !lists ? 0.34e-9 : (f->P.numerics_fast ? 0.11e-9 : 0.20e-9);
+    const double ratio = (c_bin * n_here + (f->shard ? 0.5e-3 : 1.0e-4)) / (c_step * n_here);
     float skin = std::min(sqrtf((float)(1.9 * ratio) * delta * reach), reach / 8.0f);
     if (!(skin > 0.0f) || !std::isfinite(skin) || skin / 2.0f / delta < 2.0f) skin = 0.0f;
     {
@@ -307,15 +335,15 @@ int fit_grid(fp_flock *f) {
     g.inv_cell_z = (float)((double)g.zspan / cell);
     for (int a = 0; a < 3; ++a) g.origin[a] = lo[a];
     {
-        // FP_GRID_CENTER=1 (tuning, not yet run on hardware): centre the grid on the flock instead of
-        // anchoring it at the minimum corner.  When the extent is a hair over a whole number of cells
-        // the anchored grid ends in a sliver row holding a handful of boids spread over all of z; the
-        // CTA that holds them has nine intervals spanning whole rows, overflows the tile and takes the
-        // slow global-memory path (C3 at skin 0.28: 53 of 8192 CTAs, emulated on the CPU and seen on
-        // the GPU; 0 when centred: every edge cell is then at least half a cell wide).
+        // The grid is centred on the flock rather than anchored at its minimum corner.  When the extent
+        // is a hair over a whole number of cells an anchored grid ends in a sliver row holding a handful
+        // of boids spread over all of z; the CTA that holds them has nine intervals spanning whole rows,
+        // overflows the tile and takes the slow global-memory path (C3 at skin 0.28: 53 of 8192 CTAs,
+        // emulated on the CPU and seen on the GPU; 0 when centred: every edge cell is then at least half
+        // a cell wide.  Measured: C3 0.261 -> 0.253 ms/step).  FP_GRID_CENTER=0 anchors it (tuning).
         static const bool center = [] {
             const char *e = getenv("FP_GRID_CENTER");
-            return e && atoi(e) != 0;
+            return !(e && *e == '0');
         }();
         if (center)
             for (int a = 0; a < 3; ++a) {
@@ -415,15 +443,23 @@ int ensure_caller_order(fp_flock *f) {
     return FP_OK;
 }
 
-void select_leads(fp_flock *f) {
+// the lead rows of the step about to be enqueued -> f->P; returns the version it runs with
+// (a replayed step takes the version it was first enqueued under)
+uint32_t select_leads(fp_flock *f) {
+    uint32_t ver = f->lead_ver;
+    if (!f->replay_lead_vers.empty()) {
+        ver = f->replay_lead_vers.front();
+        f->replay_lead_vers.erase(f->replay_lead_vers.begin());
+    }
     if (f->d_lead_table && f->table_rows) {
         const uint32_t row = std::min(f->table_cursor, f->table_rows - 1);
         f->P.leads = f->d_lead_table + (size_t)row * f->table_leads * 8;
         f->P.n_leads = (int)f->table_leads;
     } else {
-        f->P.leads = f->d_leads;
+        f->P.leads = f->n_leads ? f->d_lead_ring + (size_t)(ver % fp_flock::LEAD_RING) * f->n_leads * 8 : nullptr;
         f->P.n_leads = (int)f->n_leads;
     }
+    return ver;
 }
 
 bool refit_due(const fp_flock *f) {
@@ -472,37 +508,25 @@ WalkIO walk_io(fp_flock *f, bool stepping) {
     return io;
 }
 
-// ---- standing candidate lists (fp_walk_nl.cu): experimental ----------------------------------
-// FP_WALK_VARIANT=41: single-GPU grid flocks (checked on a B200 against the production walk,
-// DESIGN.md 4.2); 42: sharded grid flocks as well (same kernels over the owned slots of a slab);
-// 43: as 41 with the build's stores staged through shared memory; 44: as 41 with 48-entry survivor
-// lists and six CTAs per SM; 45: as 43 with a CTA's boids handed to its threads in order of list
-// length; 46: as 41, building only for binnings that live (see nl_prepare); 47: 43 .. 46 together.
-// 42 .. 47 have not run on hardware yet.
+// ---- standing candidate lists (fp_walk_nl.cu) ------------------------------------------------
+// The default form of a grid step, single GPU and sharded alike: FP_NL=0 turns them off (plain
+// staged walk every step; same bits under EXACT numerics).
 constexpr uint32_t NL_VCAP = 96;  // C3 / C4 density: 34 candidates per boid on average, ~70 at most
 
-int nl_variant() {
-    static const int variant = [] {
-        const char *e = getenv("FP_WALK_VARIANT");
-        return e ? atoi(e) : 0;
+bool nl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("FP_NL");
+        return !(e && *e == '0');
     }();
-    return variant;
+    return on;
 }
-
-int nl_form() {  // which form of the kernels the variant asks for (build and walk alike)
-    switch (nl_variant()) {
-        case 43: return NL_FORM_STAGED;
-        case 44: return NL_FORM_SIX_CTAS;
-        case 45: return NL_FORM_SORTED | NL_FORM_STAGED;
-        case 47: return NL_FORM_SORTED | NL_FORM_STAGED | NL_FORM_SIX_CTAS;
-        default: return NL_FORM_PLAIN;
-    }
+bool nl_trace() {
+    static const bool on = getenv("FP_NL_TRACE") != nullptr;
+    return on;
 }
 
 bool nl_wanted(const fp_flock *f) {
-    const int variant = nl_variant();
-    const bool on = f->shard ? variant == 42 : (variant >= 41 && variant <= 47);
-    return on && !f->nl_off && f->grid.skin > 0.0f;  // (no skin = a binning per step: nothing to re-use)
+    return nl_enabled() && !f->nl_off && f->grid.skin > 0.0f;  // (no skin = a binning per step: nothing to re-use)
 }
 
 void nl_free(fp_flock *f) {
@@ -527,23 +551,23 @@ int nl_ensure(fp_flock *f, uint32_t rows) {
     FP_CUDA(cudaMemsetAsync(f->nl_entries, 0, entries * sizeof(uint16_t), f->stream));
     FP_CUDA(cudaMemsetAsync(f->nl_flag, 0, sizeof(unsigned), f->stream));
     f->nl_rows = cap;
-    if (getenv("FP_NL_TRACE")) fprintf(stderr, "fp: candidate lists on (%u boids, %u entries each)\n", rows, NL_VCAP);
+    if (nl_trace()) fprintf(stderr, "fp: candidate lists on (%u boids, %u entries each)\n", rows, NL_VCAP);
     return FP_OK;
 }
 
 // Before a new build: how did the last one go?  CTAs without lists walk from global memory, which
-// is far slower than the production kernel; when more than 1 in 32 had none (and more than a
-// handful), the flock is too dense for lists of this size and the production walk takes over
-// (until a new state / config arrives).
+// is far slower than the staged walk; when more than 1 in 32 had none (and more than a handful),
+// the flock is too dense for lists of this size and the staged walk takes over (until a new
+// state / config arrives).
 int nl_review(fp_flock *f) {
     if (!f->nl_flag) return FP_OK;
     unsigned none = 0;
     FP_CUDA(cudaMemcpyAsync(&none, f->nl_flag, sizeof(none), cudaMemcpyDeviceToHost, f->stream));
     FP_CUDA(cudaStreamSynchronize(f->stream));  // (a binning has just settled: the stream is all but idle)
     FP_CUDA(cudaMemsetAsync(f->nl_flag, 0, sizeof(none), f->stream));
-    if (getenv("FP_NL_TRACE") && none) fprintf(stderr, "fp: %u CTAs without candidate lists in the last build\n", none);
+    if (nl_trace() && none) fprintf(stderr, "fp: %u CTAs without candidate lists in the last build\n", none);
     if (none > 8 && (uint64_t)none * 32u > ((uint64_t)f->nl_built_rows + 127u) / 128u) {
-        if (getenv("FP_NL_TRACE")) fprintf(stderr, "fp: candidate lists off\n");
+        if (nl_trace()) fprintf(stderr, "fp: candidate lists off\n");
         f->nl_off = true;
     }
     return FP_OK;
@@ -556,6 +580,7 @@ NlIO nl_io(const fp_flock *f, double skins = 1.0) {
     nl.cta_tab = f->nl_cta_tab;
     nl.flag = f->nl_flag;
     nl.vcap = NL_VCAP;
+    nl.tile_cap = nl_tile_cap(f->P.numerics_fast != 0);
     // every pair within reach while the binning stands was within reach + skin when it was made
     // (skins = 2: within reach + 2 skin at any other moment of the binning's life)
     const double R = (double)reach_of(f->cfg) + skins * (double)f->grid.skin;
@@ -563,46 +588,56 @@ NlIO nl_io(const fp_flock *f, double skins = 1.0) {
     return nl;
 }
 
-// Called once per step, after the binning / gate and before the walk: builds the lists when the
-// flock has just been binned (by this step, or by a tap since the last step -- either way the
-// positions are still the binned ones) and the lists on hand describe an older binning.
-//
-// Variant 46 (not yet run on hardware) builds only for binnings that live: a caller that hands over
-// a new state every step bins every step, and build + list walk is slower than the production walk
-// alone.  At once when the previous binning served >= 8 steps; otherwise at the binning's SECOND
-// step, from the positions of that moment -- every boid is within skin / 2 of its binned position
-// throughout, hence within skin of where it stands at the build: the cut becomes reach + 2 skin.
+// lists for the standing binning, from the positions as they are now
+int nl_build_now(fp_flock *f, const GridDesc &g, const WalkIO &io, double skins) {
+    int rc = nl_review(f);  // (may turn the lists off)
+    if (rc || !nl_wanted(f)) return rc;
+    const uint32_t rows = io.last - io.first;
+    if ((rc = nl_ensure(f, rows)) || (rc = launch_nl_build(f->stream, g, io, nl_io(f, skins)))) return rc;
+    f->nl_serial = f->stat_rebins;
+    f->nl_built_rows = rows;
+    return FP_OK;
+}
+
+// Called once per step, after the binning / gate and before the walk.  Lists are built only for
+// binnings that live: a caller that hands over a new state every step bins every step, and a build
+// plus a list walk is slower than the staged walk alone.  At once when the previous binning served
+// >= 8 steps; otherwise at the binning's SECOND step, from the positions of that moment -- every
+// boid is within skin / 2 of its binned position throughout, hence within skin of where it stands
+// at the build: the cut becomes reach + 2 skin.
 int nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) {
     if (!nl_wanted(f) || f->nl_serial == f->stat_rebins) return FP_OK;
     double skins = 1.0;
-    if (nl_variant() != 46 && nl_variant() != 47) {
-        if (!f->nl_fresh) return FP_OK;
-    } else if (f->nl_fresh) {
+    if (f->nl_fresh) {
         if (f->nl_prev_bin_steps < 8) return FP_OK;  // short-lived so far: see whether a second step comes
     } else if (f->nl_bin_steps == 1) {
         skins = 2.0;
     } else {
         return FP_OK;
     }
-    int rc = nl_review(f);  // (may turn the lists off)
-    if (rc || !nl_wanted(f)) return rc;
-    const uint32_t rows = io.last - io.first;
-    const float sort_params[3] = {f->P.m2_cut_hi, f->P.fov_kh, f->P.fov_kl};
-    if ((rc = nl_ensure(f, rows)) ||
-        (rc = launch_nl_build(f->stream, g, io, nl_io(f, skins), nl_form(), sort_params)))
-        return rc;
-    f->nl_serial = f->stat_rebins;
-    f->nl_built_rows = rows;
-    return FP_OK;
+    return nl_build_now(f, g, io, skins);
 }
 
-// the step's walk: on the lists when they describe the standing binning, else the production kernel
-int nl_or_production_walk(fp_flock *f, const GridDesc &g, const WalkIO &io) {
+// the step's walk: on the lists when they describe the standing binning, else the staged walk
+int nl_or_plain_walk(fp_flock *f, const GridDesc &g, const WalkIO &io) {
     f->nl_fresh = false;
     ++f->nl_bin_steps;
     if (nl_wanted(f) && f->nl_serial == f->stat_rebins)
-        return launch_nl_walk(f->stream, f->P, g, io, nl_io(f), f->d_status, nl_form());
+        return launch_nl_walk(f->stream, f->P, g, TAP_STEP, io, nl_io(f), f->d_status, TapOut{});
     return launch_grid_walk(f->stream, f->P, g, TAP_STEP, io, f->d_status, TapOut{});
+}
+
+// a tap's walk over a flock that has just been binned.  The acceleration tap of a FAST-numerics
+// flock runs the arithmetic its steps run (lists built on the spot), so that the parity checks
+// measure what is shipped; everything else is evaluated by the exact kernels.
+int tap_walk(fp_flock *f, const GridDesc &g, int tap, const WalkIO &io, const TapOut &out) {
+    if (tap == TAP_ACCEL && f->P.numerics_fast && nl_wanted(f)) {
+        int rc = FP_OK;
+        if (f->nl_serial != f->stat_rebins && (rc = nl_build_now(f, g, io, 1.0))) return rc;
+        if (nl_wanted(f) && f->nl_serial == f->stat_rebins)
+            return launch_nl_walk(f->stream, f->P, g, TAP_ACCEL, io, nl_io(f), f->d_status, out);
+    }
+    return launch_grid_walk(f->stream, f->P, g, tap, io, f->d_status, out);
 }
 
 // timing hook: record the next pooled event on the stream (no-op unless timing)
@@ -630,17 +665,17 @@ int grid_steps(fp_flock *f, uint32_t nsteps) {
         // a binning never runs inside a window the device may have voided: settle first (one
         // host sync per binning, i.e. every few dozen steps; it also refreshes the plan)
         if ((!f->bin_valid || f->plan_left <= 0) && (rc = settle(f))) return rc;
-        select_leads(f);
+        const uint32_t lead_ver = select_leads(f);
         if ((rc = mark_event(f))) return rc;
-        f->pending.push_back({f->ordinal, f->cur, f->work.soa_cur, f->table_cursor, f->steps_since_fit, 0u});
+        f->pending.push_back({f->ordinal, f->cur, f->work.soa_cur, f->table_cursor, f->steps_since_fit, 0u, lead_ver});
         if (!f->bin_valid || f->plan_left <= 0) {
             if ((rc = grid_rebin(f))) return rc;
         } else if ((rc = launch_skin_gate(f->stream, f->work.ctl, f->ordinal, 0, f->P.dt, f->skin_budget))) {
             return rc;
         }
-        if ((rc = nl_prepare(f, f->grid, walk_io(f, true)))) return rc;  // (experimental; no-op by default)
+        if ((rc = nl_prepare(f, f->grid, walk_io(f, true)))) return rc;  // (its build counts as sort phase)
         if ((rc = mark_event(f))) return rc;
-        if ((rc = nl_or_production_walk(f, f->grid, walk_io(f, true)))) return rc;
+        if ((rc = nl_or_plain_walk(f, f->grid, walk_io(f, true)))) return rc;
         f->cur ^= 1;
         f->work.soa_cur ^= 1;
         if ((rc = mark_event(f))) return rc;
@@ -682,6 +717,12 @@ int settle(fp_flock *f) {
         }
         const fp_flock::Pending at = f->pending[k];
         const uint32_t redo = (uint32_t)(f->pending.size() - k);
+        {   // versions of the steps to redo, ahead of whatever an enclosing replay still has to enqueue
+            std::vector<uint32_t> vers;
+            for (size_t q = k; q < f->pending.size(); ++q) vers.push_back(f->pending[q].lead_ver);
+            vers.insert(vers.end(), f->replay_lead_vers.begin(), f->replay_lead_vers.end());
+            f->replay_lead_vers.swap(vers);
+        }
         f->pending.clear();
         f->cur = at.cur;
         f->work.soa_cur = at.soa_cur;
@@ -708,12 +749,13 @@ int run_tap(fp_flock *f, int tap, const TapOut &out) {
         int rc;
         if (refit_due(f) && (rc = fit_grid(f))) return rc;
         if ((rc = grid_rebin(f))) return rc;
-        return launch_grid_walk(f->stream, f->P, f->grid, tap, walk_io(f, false), f->d_status, out);
+        return tap_walk(f, f->grid, tap, walk_io(f, false), out);
     }
     int rc = ensure_caller_order(f);
     if (rc) return rc;
+    if (f->P.numerics_fast && (rc = launch_bounds(f->stream, f->pos[f->cur], nullptr, f->n, f->d_bounds))) return rc;
     return launch_allpairs(f->stream, f->P, tap, f->pos[f->cur], f->vel[f->cur], f->n, 0, f->n, nullptr,
-                           nullptr, f->d_status, out);
+                           nullptr, f->d_status, out, 0, f->d_bounds);
 }
 
 }  // namespace
@@ -723,8 +765,11 @@ namespace fp {
 int flock_fit_grid(fp_flock *f) { return fit_grid(f); }
 int flock_nl_prepare(fp_flock *f, const GridDesc &g, const WalkIO &io) { return nl_prepare(f, g, io); }
 void flock_nl_binned(fp_flock *f) { nl_binned(f); }
-int flock_step_walk(fp_flock *f, const GridDesc &g, const WalkIO &io) { return nl_or_production_walk(f, g, io); }
-void flock_select_leads(fp_flock *f) { select_leads(f); }
+int flock_step_walk(fp_flock *f, const GridDesc &g, const WalkIO &io) { return nl_or_plain_walk(f, g, io); }
+int flock_tap_walk(fp_flock *f, const GridDesc &g, int tap, const WalkIO &io, const TapOut &out) {
+    return tap_walk(f, g, tap, io, out);
+}
+uint32_t flock_select_leads(fp_flock *f) { return select_leads(f); }
 int64_t flock_plan_steps(const fp_flock *f, float D, float first_delta) { return plan_steps(f, D, first_delta); }
 float flock_plan_delta(float v2max, float pmax, float dt) { return plan_delta(v2max, pmax, dt); }
 }  // namespace fp
@@ -732,6 +777,12 @@ float flock_plan_delta(float v2max, float pmax, float dt) { return plan_delta(v2
 namespace fp {
 int flock_allpairs_step(fp_flock *f, const float4 *pos_all, const float4 *vel_all, uint32_t n_all, uint32_t row0,
                         uint32_t nrows, float4 *pos_out, float4 *vel_out) {
+    if (f->P.numerics_fast) {  // one kernel; its pre-gate needs the flock's bounds (device side, no host sync)
+        int rc = launch_bounds(f->stream, pos_all, nullptr, n_all, f->d_bounds);
+        if (rc) return rc;
+        return launch_allpairs(f->stream, f->P, TAP_STEP, pos_all, vel_all, n_all, row0, nrows, pos_out, vel_out,
+                               f->d_status, TapOut{}, 0, f->d_bounds);
+    }
     if (f->ap_choice >= 0 && ++f->ap_age >= 1024) {  // the flock may have changed density: measure again
         f->ap_choice = -1;
         f->ap_probe = 0;
@@ -813,7 +864,14 @@ static int create_common(fp_flock **out, const fp_config *cfg, uint64_t n_global
     f->n_global = n_global;
     f->first_index = (uint32_t)first;
     if (cfg) f->cfg = *cfg; else fp_config_default(&f->cfg);
-    derive_params(f->cfg, f->P);
+    {
+        static const int env_numerics = [] {  // FP_NUMERICS=fast|exact: the default of new handles (tuning)
+            const char *e = getenv("FP_NUMERICS");
+            return e && (*e == 'f' || *e == 'F' || *e == '1') ? FP_NUMERICS_FAST : FP_NUMERICS_EXACT;
+        }();
+        f->numerics = env_numerics;
+    }
+    derive_params(f->cfg, f->P, f->numerics == FP_NUMERICS_FAST);
     int rc = FP_OK;
     auto fail = [&](int code) { fp_flock_destroy(f); return code; };
     if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -876,7 +934,9 @@ int fp_flock_destroy(fp_flock *f) {
     if (f->stream) cudaStreamSynchronize(f->stream);
     if (f->shard) shard_destroy(f->shard);
     for (int b = 0; b < 2; ++b) { dev_free(f->pos[b]); dev_free(f->vel[b]); }
-    dev_free(f->d_leads); dev_free(f->d_attr); dev_free(f->d_obs); dev_free(f->d_lead_table);
+    dev_free(f->d_lead_ring); dev_free(f->d_attr); dev_free(f->d_obs); dev_free(f->d_lead_table);
+    if (f->h_lead_stage) cudaFreeHost(f->h_lead_stage);
+    for (auto &ev : f->lead_ev) if (ev) cudaEventDestroy(ev);
     dev_free(f->d_status); dev_free(f->d_census); dev_free(f->d_bounds);
     free_grid_work(f);
     nl_free(f);
@@ -897,7 +957,7 @@ int fp_flock_set_config(fp_flock *f, const fp_config *cfg) {
     if (!cfg) { set_error("null config"); return FP_ERR_INVALID; }
     const float old_reach = reach_of(f->cfg);
     f->cfg = *cfg;
-    derive_params(f->cfg, f->P);
+    derive_params(f->cfg, f->P, f->numerics == FP_NUMERICS_FAST);
     if (reach_of(f->cfg) != old_reach) f->grid_valid = false;
     f->bin_valid = false;  // dt and reach enter the skin accounting
     f->nl_off = false;
@@ -923,6 +983,30 @@ int fp_flock_set_method(fp_flock *f, int method) {
     return FP_OK;
 }
 
+int fp_flock_set_numerics(fp_flock *f, int numerics) {
+    if (!f || (numerics != FP_NUMERICS_EXACT && numerics != FP_NUMERICS_FAST)) {
+        set_error("bad numerics");
+        return FP_ERR_INVALID;
+    }
+    int rc = check(f);
+    if (rc) return rc;
+    if (numerics == f->numerics) return FP_OK;
+    f->numerics = numerics;
+    derive_params(f->cfg, f->P, numerics == FP_NUMERICS_FAST);
+    f->bin_valid = false;  // the lists on hand were sized for the other walk's tile
+    f->nl_serial = ~0ull;
+    f->ap_choice = -1;
+    f->ap_probe = 0;
+    return FP_OK;
+}
+
+int fp_flock_get_numerics(fp_flock *f, int *numerics, int *in_use) {
+    if (!f) { set_error("null flock handle"); return FP_ERR_INVALID; }
+    if (numerics) *numerics = f->numerics;
+    if (in_use) *in_use = f->P.numerics_fast ? FP_NUMERICS_FAST : FP_NUMERICS_EXACT;
+    return FP_OK;
+}
+
 int fp_flock_get_method(fp_flock *f, int *method_in_use) {
     if (!f || !method_in_use) { set_error("null argument"); return FP_ERR_INVALID; }
     if (f->shard) *method_in_use = shard_method(f->shard, f->method, f->cfg);
@@ -931,16 +1015,45 @@ int fp_flock_get_method(fp_flock *f, int *method_in_use) {
 }
 
 int fp_flock_set_leads(fp_flock *f, uint32_t n_leads, const float *leads7) {
-    int rc = check(f);
+    // (no settle: the steps in flight keep the rows they were enqueued with -- see fp_flock.h)
+    int rc = check(f, false);
     if (rc) return rc;
     if (n_leads && !leads7) { set_error("null leads"); return FP_ERR_INVALID; }
-    std::vector<float> padded((size_t)n_leads * 8, 0.0f);
-    for (uint32_t k = 0; k < n_leads; ++k) memcpy(&padded[8 * k], leads7 + 7 * k, 7 * sizeof(float));
-    rc = upload_table(f, &f->d_leads, padded.data(), padded.size());
-    if (rc) return rc;
-    f->n_leads = n_leads;
-    dev_free(f->d_lead_table);  // a plain table replaces any per-step table
-    f->table_rows = f->table_leads = f->table_cursor = 0;
+    constexpr uint32_t RING = fp_flock::LEAD_RING, STAGES = fp_flock::LEAD_STAGES;
+    const size_t stride = (size_t)n_leads * 8;
+    const bool relayout = n_leads != f->n_leads || (n_leads && !f->d_lead_ring) || f->d_lead_table;
+    if (relayout || (!f->pending.empty() && f->lead_ver + 1 - f->pending.front().lead_ver >= RING - 1)) {
+        if ((rc = settle(f))) return rc;  // nothing in flight refers to the rows any more
+    }
+    if (relayout) {
+        FP_CUDA(cudaStreamSynchronize(f->stream));
+        dev_free(f->d_lead_ring);
+        if (f->h_lead_stage) cudaFreeHost(f->h_lead_stage);
+        f->h_lead_stage = nullptr;
+        if (n_leads) {
+            if ((rc = dev_alloc(&f->d_lead_ring, stride * RING))) return rc;
+            FP_CUDA(cudaMallocHost((void **)&f->h_lead_stage, stride * STAGES * sizeof(float)));
+            for (auto &e : f->lead_ev)
+                if (!e) FP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        dev_free(f->d_lead_table);  // a plain table replaces any per-step table
+        f->table_rows = f->table_leads = f->table_cursor = 0;
+        f->n_leads = n_leads;
+    }
+    if (n_leads) {
+        ++f->lead_ver;
+        const uint32_t st = f->lead_stage_cur++ % STAGES;
+        FP_CUDA(cudaEventSynchronize(f->lead_ev[st]));  // the copy that last used this staging slot
+        float *h = f->h_lead_stage + (size_t)st * stride;
+        for (uint32_t k = 0; k < n_leads; ++k) {
+            memcpy(h + 8 * k, leads7 + 7 * k, 7 * sizeof(float));
+            h[8 * k + 7] = 0.0f;
+        }
+        FP_CUDA(cudaMemcpyAsync(f->d_lead_ring + (size_t)(f->lead_ver % RING) * stride, h, stride * sizeof(float),
+                                cudaMemcpyHostToDevice, f->stream));
+        FP_CUDA(cudaEventRecord(f->lead_ev[st], f->stream));
+    }
+    f->d_leads = n_leads ? f->d_lead_ring + (size_t)(f->lead_ver % RING) * stride : nullptr;
     refresh_tables(f);
     return FP_OK;
 }
@@ -952,7 +1065,9 @@ int fp_flock_set_lead_table(fp_flock *f, uint32_t steps, uint32_t n_leads, const
     const size_t rows = (size_t)steps * n_leads;
     std::vector<float> padded(rows * 8, 0.0f);
     for (size_t k = 0; k < rows; ++k) memcpy(&padded[8 * k], table7 + 7 * k, 7 * sizeof(float));
-    rc = upload_table(f, &f->d_lead_table, padded.data(), padded.size());
+    dev_free(f->d_lead_table);
+    size_t table_cap = 0;
+    rc = upload_table(f, &f->d_lead_table, &table_cap, padded.data(), padded.size());
     if (rc) return rc;
     f->table_rows = n_leads ? steps : 0;
     f->table_leads = n_leads;
@@ -964,7 +1079,7 @@ int fp_flock_set_attractors(fp_flock *f, uint32_t n, const float *a4) {
     int rc = check(f);
     if (rc) return rc;
     if (n && !a4) { set_error("null attractors"); return FP_ERR_INVALID; }
-    rc = upload_table(f, &f->d_attr, a4, (size_t)n * 4);
+    rc = upload_table(f, &f->d_attr, &f->attr_cap, a4, (size_t)n * 4);
     if (rc) return rc;
     f->n_attr = n;
     refresh_tables(f);
@@ -975,7 +1090,7 @@ int fp_flock_set_obstacles(fp_flock *f, uint32_t n, const float *o4) {
     int rc = check(f);
     if (rc) return rc;
     if (n && !o4) { set_error("null obstacles"); return FP_ERR_INVALID; }
-    rc = upload_table(f, &f->d_obs, o4, (size_t)n * 4);
+    rc = upload_table(f, &f->d_obs, &f->obs_cap, o4, (size_t)n * 4);
     if (rc) return rc;
     f->n_obs = n;
     refresh_tables(f);
@@ -1041,6 +1156,7 @@ int fp_flock_rebin_info(fp_flock *f, float *skin, uint64_t *grid_steps, uint64_t
 }
 
 static int mark(fp_flock *f) { return mark_event(f); }
+
 }  // extern "C"
 namespace fp {
 int flock_mark(fp_flock *f) { return mark_event(f); }
@@ -1201,6 +1317,25 @@ static int read_instances(fp_flock *f, float *out, int raw) {
     FP_CUDA(cudaStreamSynchronize(f->stream));
     return FP_OK;
 }
+int fp_flock_export_instances(fp_flock *f, void *dst, int raw) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (f->shard) { set_error("instance export of a sharded flock: use fp_flock_read_local"); return FP_ERR_UNSUPPORTED; }
+    if (!f->n) return FP_OK;
+    if (!dst) { set_error("null output"); return FP_ERR_INVALID; }
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, dst) != cudaSuccess || at.type == cudaMemoryTypeUnregistered ||
+        !at.devicePointer) {
+        cudaGetLastError();
+        set_error("export_instances: the destination is not addressable by the device (pageable host memory?)");
+        return FP_ERR_INVALID;
+    }
+    if ((rc = launch_instances(f->stream, f->pos[f->cur], f->vel[f->cur], (float *)at.devicePointer, f->n,
+                               f->first_index, raw ? 1 : 0)))
+        return rc;
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    return FP_OK;
+}
 int fp_flock_read_instances(fp_flock *f, float *out8) { return read_instances(f, out8, 0); }
 int fp_flock_read_instances_raw(fp_flock *f, float *out25) { return read_instances(f, out25, 1); }
 
@@ -1259,7 +1394,8 @@ int fp_flock_pair_census(fp_flock *f, uint64_t out4[4]) {
 }
 
 int fp_flock_device_state(fp_flock *f, const void **pos4, const void **vel4) {
-    if (!f) { set_error("null flock handle"); return FP_ERR_INVALID; }
+    int rc = check(f);  // settles: the pointers describe steps that have happened
+    if (rc) return rc;
     if (pos4) *pos4 = f->pos[f->cur];
     if (vel4) *vel4 = f->vel[f->cur];
     return FP_OK;
@@ -1399,6 +1535,33 @@ int fp_flock_read_local(fp_flock *f, uint64_t *out_index, float *out_aos6) {
         o[0] = p[i].x; o[1] = p[i].y; o[2] = p[i].z;
         o[3] = v[i].x; o[4] = v[i].y; o[5] = v[i].z;
     }
+    return FP_OK;
+}
+
+
+int fp_flock_write_local(fp_flock *f, uint64_t n_local, const uint64_t *index, const float *state_aos6) {
+    int rc = check(f);
+    if (rc) return rc;
+    if (f->shard) return shard_write_local(f->shard, f, n_local, index, state_aos6);
+    // single GPU: the same contract over the resident order
+    if (n_local != f->n) { set_error("write_local: row count differs from fp_flock_len"); return FP_ERR_INVALID; }
+    if (!f->n) return FP_OK;
+    if (!index || !state_aos6) { set_error("null input"); return FP_ERR_INVALID; }
+    std::vector<float4> p, v;
+    if ((rc = fetch_owned(f, p, v))) return rc;
+    for (size_t i = 0; i < p.size(); ++i) {
+        uint32_t u;
+        memcpy(&u, &p[i].w, 4);
+        if (u != index[i]) { set_error("write_local: index order differs from fp_flock_read_local"); return FP_ERR_INVALID; }
+        const float *s = state_aos6 + 6 * i;
+        p[i] = make_float4(s[0], s[1], s[2], p[i].w);
+        v[i] = make_float4(s[3], s[4], s[5], 0.0f);
+    }
+    FP_CUDA(cudaMemcpyAsync(f->pos[f->cur], p.data(), p.size() * sizeof(float4), cudaMemcpyHostToDevice, f->stream));
+    FP_CUDA(cudaMemcpyAsync(f->vel[f->cur], v.data(), v.size() * sizeof(float4), cudaMemcpyHostToDevice, f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    f->bin_valid = false;
+    if (!f->domain_user) f->grid_valid = false;
     return FP_OK;
 }
 

@@ -22,8 +22,19 @@ struct fp_flock {
     int cur = 0;
     bool permuted = false;
     int method = FP_METHOD_AUTO, method_in_use = FP_METHOD_ALLPAIRS;
+    int numerics = FP_NUMERICS_EXACT;
     float *d_leads = nullptr, *d_attr = nullptr, *d_obs = nullptr, *d_lead_table = nullptr;
     uint32_t n_leads = 0, n_attr = 0, n_obs = 0, table_rows = 0, table_leads = 0, table_cursor = 0;
+    // fp_flock_set_leads keeps the last LEAD_RING row sets on the device: a step enqueued under
+    // version v reads slot v % LEAD_RING, so the caller can hand over new rows before every step
+    // without the host waiting for the steps in flight (a replayed step finds the rows it ran with)
+    static constexpr uint32_t LEAD_RING = 512, LEAD_STAGES = 8;
+    float *d_lead_ring = nullptr;          // LEAD_RING x n_leads x 8 floats; d_leads points into it
+    float *h_lead_stage = nullptr;         // pinned, LEAD_STAGES x n_leads x 8
+    cudaEvent_t lead_ev[LEAD_STAGES] = {}; // the copy out of each staging slot
+    uint32_t lead_ver = 0, lead_stage_cur = 0;
+    std::vector<uint32_t> replay_lead_vers;  // versions of the steps being replayed (front first)
+    size_t attr_cap = 0, obs_cap = 0;      // floats allocated behind d_attr / d_obs
     unsigned *d_status = nullptr;
     unsigned long long *d_census = nullptr;
     float *d_bounds = nullptr;
@@ -46,6 +57,7 @@ struct fp_flock {
         uint32_t table_cursor;
         uint64_t steps_since_fit;
         uint32_t steps_since_bin;
+        uint32_t lead_ver;
     };
     std::vector<Pending> pending;
     fp::SkinCtl *h_ctl = nullptr;  // pinned read-back of work.ctl
@@ -53,7 +65,7 @@ struct fp_flock {
     uint32_t timed_steps = 0;
     float skin_override = -1.0f;  // < 0: sized from the flock's speed at every fit
     float plan_scale = 1.0f;      // stretches the planned steps per binning (tests)
-    // standing candidate lists (fp_walk_nl.cu; experimental, FP_WALK_VARIANT=41 / 42)
+    // standing candidate lists (fp_walk_nl.cu)
     uint16_t *nl_entries = nullptr, *nl_count = nullptr;
     uint32_t *nl_cta_tab = nullptr;
     unsigned *nl_flag = nullptr;

@@ -13,8 +13,8 @@
 // the cell edge carries a skin, and a boid's home cell is the key its slot was
 // binned under.  The state stays in sorted order (pos.w carries the caller
 // index), so every global access is coalesced.  This file holds the binning
-// kernels and the simple walk forms (taps, cross-checks); the production walk
-// is fp_walk.cu.
+// kernels and the one-phase walk of the neighbour-set / census taps; steps run
+// on standing candidate lists (fp_walk_nl.cu) or the staged walk (fp_walk.cu).
 #include <stdlib.h>
 
 #include "fp_grid.cuh"
@@ -168,135 +168,18 @@ grid_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned 
     walk_finish<TAP>(P, s, pi4, vi4, self, acc, n_count, n_hash, io, status, tap);
 }
 
-// Three-phase form reading candidates from global memory (kept as a cross-check of the staged
-// production kernel in fp_walk.cu, FP_WALK_VARIANT=2): same arithmetic, same summation order.
-//   1. gate   -- every candidate: m2 against m2_cut; survivors' slots are appended to
-//                a per-thread list in shared memory ([entry][thread]: bank == lane);
-//   2. FOV    -- survivors only: exact cosine against cstar; list compacted in place;
-//   3. forces -- visible neighbours only: pair_inrange, accumulated in list (= slot) order.
-constexpr int W2_BLOCK = 128;
-constexpr int W2_CAP = 64;
-
-template <int TAP>
-__global__ void __launch_bounds__(W2_BLOCK)
-grid_walk2_kernel(const DevParams P, const GridDesc g, const WalkIO io, unsigned *__restrict__ status,
-                  TapOut tap) {
-    if (TAP == TAP_STEP && io.ctl && io.ctl->stale) return;
-    __shared__ uint32_t list[W2_CAP][W2_BLOCK];
-    const float4 *__restrict__ pos_s = io.pos_s;
-    const float4 *__restrict__ vel_s = io.vel_s;
-    const uint32_t *__restrict__ cell_start = io.cell_start;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t s = io.first + blockIdx.x * W2_BLOCK + tid;
-    const bool active = s < io.last;
-    float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
-    Self self;
-    self.p = self.v = self.vhat = v3zero();
-    bool work = false;
-    int cx = 0, cy = 0, cz = 0;
-    if (active) {
-        pi4 = pos_s[s];
-        vi4 = vel_s[s];
-    }
-    if (TAP == TAP_STEP && io.ctl) track_motion(io.ctl, active, pi4, vi4);
-    if (active) {
-        self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
-        const bool ghost = __float_as_uint(vi4.w) != 0u;
-        work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
-        home_cell(g, __ldg(io.home + (s - io.first)), cx, cy, cz);
-    }
-    V3 acc = v3zero();
-    int cnt = 0;
-
-    auto drain = [&]() {
-        int nb = 0;
-        for (int k = 0; k < cnt; ++k) {  // phase 2
-            const uint32_t j = list[k][tid];
-            const float4 pj = __ldg(pos_s + j);
-            V3 d;
-            const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
-            if (!pair_fov_culled(self, d, m2, P.cstar)) list[nb++][tid] = j;
-        }
-        for (int k = 0; k < nb; ++k) {  // phase 3
-            const uint32_t j = list[k][tid];
-            const float4 pj = __ldg(pos_s + j);
-            const float4 vj = __ldg(vel_s + j);
-            V3 d, contrib;
-            const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
-            if (pair_flock(P, self, d, m2, v3(vj.x, vj.y, vj.z), contrib))
-                acc = vadd(acc, contrib);
-        }
-        cnt = 0;
-    };
-
-    const int z0 = max(cz - g.zspan, 0), z1 = min(cz + g.zspan, g.dim[2] - 1);
-#pragma unroll 1
-    for (int dx = -1; dx <= 1; ++dx) {
-#pragma unroll 1
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int x = cx + dx, y = cy + dy;
-            uint32_t jb = 0, je = 0;
-            if (work && x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1]) {
-                const uint32_t rowbase = row_base(g, x, y);
-                jb = __ldg(cell_start + rowbase + z0);
-                je = __ldg(cell_start + rowbase + z1 + 1);
-            }
-            const uint32_t nchunk = __reduce_max_sync(0xffffffffu, (je - jb + W2_CAP - 1) / W2_CAP);
-            for (uint32_t c = 0; c < nchunk; ++c) {
-                const uint32_t j0 = min(jb + c * W2_CAP, je), j1 = min(j0 + W2_CAP, je);
-                if (__any_sync(0xffffffffu, cnt + (int)(j1 - j0) > W2_CAP)) drain();
-#pragma unroll 4
-                for (uint32_t j = j0; j < j1; ++j) {  // phase 1
-                    const float4 pj = __ldg(pos_s + j);
-                    V3 d;
-                    const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
-                    if (!(m2 >= P.m2_cut)) list[cnt++][tid] = j;
-                }
-            }
-        }
-    }
-    drain();
-    if (!active) return;
-    walk_finish<TAP>(P, s, pi4, vi4, self, acc, 0u, 0ull, io, status, tap);
-}
-
 int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, const WalkIO &io,
                      unsigned *status, const TapOut &tap_out) {
     if (io.last <= io.first) return FP_OK;
-    // FP_WALK_VARIANT (debug/tuning): 1 = one-phase, 2 = three-phase from global memory,
-    // 31.. = TMA-staged three-phase tile shapes (fp_walk.cu).  Default: staged.
-    static const int variant = [] {
-        const char *e = getenv("FP_WALK_VARIANT");
-        return e ? atoi(e) : 31;
-    }();
+    // steps and the acceleration tap: the staged walk (fp_walk.cu); neighbour sets and the census:
+    // the one-phase kernel above, which evaluates every predicate for every candidate
+    if (tap == TAP_STEP || tap == TAP_ACCEL) return launch_grid_walk3(st, P, g, tap, io, status, tap_out);
     const uint32_t rows = io.last - io.first;
     const dim3 grid((rows + WALK_BLOCK - 1) / WALK_BLOCK), block(WALK_BLOCK);
-    const dim3 grid2((rows + W2_BLOCK - 1) / W2_BLOCK), block2(W2_BLOCK);
-    if ((tap == TAP_STEP || tap == TAP_ACCEL) && variant >= 30)
-        return launch_grid_walk3(st, P, g, tap, variant, io, status, tap_out);
-    if ((tap == TAP_STEP || tap == TAP_ACCEL) && variant == 1) {
-        if (tap == TAP_STEP)
-            grid_walk_kernel<TAP_STEP><<<grid, block, 0, st>>>(P, g, io, status, tap_out);
-        else
-            grid_walk_kernel<TAP_ACCEL><<<grid, block, 0, st>>>(P, g, io, status, tap_out);
-        count_launch();
-        FP_CUDA(cudaGetLastError());
-        return FP_OK;
-    }
-    switch (tap) {
-        case TAP_STEP:
-            grid_walk2_kernel<TAP_STEP><<<grid2, block2, 0, st>>>(P, g, io, status, tap_out);
-            break;
-        case TAP_ACCEL:
-            grid_walk2_kernel<TAP_ACCEL><<<grid2, block2, 0, st>>>(P, g, io, status, tap_out);
-            break;
-        case TAP_NEIGHBORS:
-            grid_walk_kernel<TAP_NEIGHBORS><<<grid, block, 0, st>>>(P, g, io, status, tap_out);
-            break;
-        default:
-            grid_walk_kernel<TAP_CENSUS><<<grid, block, 0, st>>>(P, g, io, status, tap_out);
-            break;
-    }
+    if (tap == TAP_NEIGHBORS)
+        grid_walk_kernel<TAP_NEIGHBORS><<<grid, block, 0, st>>>(P, g, io, status, tap_out);
+    else
+        grid_walk_kernel<TAP_CENSUS><<<grid, block, 0, st>>>(P, g, io, status, tap_out);
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;

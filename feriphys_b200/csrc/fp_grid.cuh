@@ -64,7 +64,7 @@ __device__ __forceinline__ void track_motion(SkinCtl *ctl, bool counts, float4 p
 
 // Shared epilogue of the walk kernels: per-boid extras (flocking.rs:105-113), Euler
 // update (flocking.rs:116-117) and the debug taps.
-template <int TAP>
+template <int TAP, bool FAST = false>
 __device__ __forceinline__ void walk_finish(const DevParams &P, uint32_t s, float4 pi4, float4 vi4,
                                             const Self &self, V3 acc, uint32_t n_count,
                                             unsigned long long n_hash, const WalkIO &io,
@@ -88,7 +88,8 @@ __device__ __forceinline__ void walk_finish(const DevParams &P, uint32_t s, floa
     }
     Extras e;
     unsigned flags = 0;
-    const V3 a = accel_total(P, self, acc, e, flags, TAP == TAP_ACCEL);
+    const V3 a = FAST ? accel_total_fast(P, self, acc, e, flags, TAP == TAP_ACCEL)
+                      : accel_total(P, self, acc, e, flags, TAP == TAP_ACCEL);
     if (TAP == TAP_ACCEL) {
         float *o = tap.accel3 + 3ull * idx;
         o[0] = a.x; o[1] = a.y; o[2] = a.z;

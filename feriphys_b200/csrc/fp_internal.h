@@ -117,7 +117,8 @@ struct WalkIO {
 // pos_all/vel_all.  For TAP_STEP writes pos_out/vel_out[0..nrows).
 int launch_allpairs(cudaStream_t st, const DevParams &P, int tap, const float4 *pos_all,
                     const float4 *vel_all, uint32_t n_all, uint32_t row0, uint32_t nrows,
-                    float4 *pos_out, float4 *vel_out, unsigned *status, const TapOut &tap_out, int variant = 0);
+                    float4 *pos_out, float4 *vel_out, unsigned *status, const TapOut &tap_out, int variant = 0,
+                    const float *bounds8 = nullptr);  // FAST numerics: launch_bounds() of pos_all (device)
 
 // One CTA, `nsteps` steps in one launch, reference summation order (fp_small.cu).
 // lead_table: nsteps rows of n_leads x 8 floats, or NULL to use P.leads for every step.
@@ -156,36 +157,31 @@ int launch_grid_reorder(cudaStream_t st, const uint32_t *vals, const float4 *pos
 int launch_grid_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, const WalkIO &io,
                      unsigned *status, const TapOut &tap_out);
 
-// TMA-staged three-phase walk (fp_walk.cu); variant selects <BLOCK, TILE_CAP, CAP>
-int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, int variant,
-                      const WalkIO &io, unsigned *status, const TapOut &tap_out);
+// TMA-staged two-phase walk (fp_walk.cu): TAP_STEP / TAP_ACCEL without candidate lists
+int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, const WalkIO &io,
+                      unsigned *status, const TapOut &tap_out);
 
-// Standing candidate lists (fp_walk_nl.cu; EXPERIMENTAL, FP_WALK_VARIANT=41, single GPU): the
-// distance pre-gate of the walk done once per binning instead of once per step.
+// Standing candidate lists (fp_walk_nl.cu): the distance pre-gate of the walk done once per
+// binning instead of once per step.  The default form of a grid step.
 struct NlIO {
     uint16_t *entries;   // [cta][vcap][128]: tile offsets (row << 12 | offset) of the candidates in reach + skin
-    uint16_t *count;     // [slot - first]: entries of each boid (NL_FORM_SORTED: [cta * 128 + thread], boid << 8 | entries)
+    uint16_t *count;     // [slot - first]: entries of each boid
     uint32_t *cta_tab;   // [cta][20]: the nine staged intervals of each CTA, [18] != 0: this CTA has no lists
-    unsigned *flag;      // [0]: CTAs the last build left without lists (tile or list overflow);
-                         // [1..3]: NL_FORM_SORTED, bits of DevParams' m2_cut_hi, fov_kh, fov_kl
+    unsigned *flag;      // [0]: CTAs the last build left without lists (tile or list overflow)
     uint32_t vcap;       // list capacity, a multiple of 4
+    uint32_t tile_cap;   // staged candidates the walk that will use the lists can hold per CTA
     float m2_wide;       // build cut: (reach + skin)^2 (1 + 1e-5)
 };
 size_t nl_entries_elems(uint32_t rows, uint32_t vcap);
 size_t nl_cta_tab_elems(uint32_t rows);
-// after a binning, before its first walk
-// Forms of the two kernels.  PLAIN is the one checked on hardware (FP_WALK_VARIANT=41); the others
-// are written but have not run yet: STAGED (43) collects the build's entries in shared memory and
-// writes whole rows; SIX_CTAS (44) walks with 48-entry survivor lists at six CTAs per SM; SORTED (45)
-// hands a CTA's boids to its threads in order of list length (build and walk must agree on it).
-// (bit flags: 47 combines them; SORTED implies STAGED)
-enum { NL_FORM_PLAIN = 0, NL_FORM_STAGED = 1, NL_FORM_SIX_CTAS = 2, NL_FORM_SORTED = 4 };
-// sort_params (NL_FORM_SORTED): DevParams' m2_cut_hi, fov_kh, fov_kl
-int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, int form = NL_FORM_PLAIN,
-                    const float sort_params[3] = nullptr);
-// a step (TAP_STEP) on the standing lists; same result as launch_grid_walk
-int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, const NlIO &nl,
-                   unsigned *status, int form = NL_FORM_PLAIN);
+uint32_t nl_tile_cap(bool fast);
+// after a binning, before the first walk that uses the lists
+int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl);
+// a step (TAP_STEP) -- or, under FAST numerics, the acceleration tap -- on the standing lists.
+// EXACT numerics: same bits as launch_grid_walk.  FAST numerics (P.numerics_fast): same neighbour
+// sets, accelerations within ~1e-6 relative.
+int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, const WalkIO &io, const NlIO &nl,
+                   unsigned *status, const TapOut &tap_out);
 
 // Lazy re-binning control (fp_misc.cu).  Runs before each grid step: on a re-binning step it
 // resets the displacement bound, otherwise it adds the last walk's bound

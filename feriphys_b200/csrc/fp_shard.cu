@@ -114,7 +114,8 @@ struct Shard {
     // current binning: records [0, n_all) = [ghost L | owned | ghost R]
     uint32_t own0 = 0, own_n = 0, n_all = 0;
     uint32_t lay_first[2] = {0, 0}, lay_last[2] = {0, 0};  // slot ranges of my first / last owned layer
-    struct Layout { uint32_t nL, nO, nR, cur, soa_cur, pad[3]; };
+    struct Layout { uint32_t nL, nO, nR, cur, soa_cur, next_fits, pad[2]; };
+    bool next_fits = true;     // every rank's NEXT binning fits its buffers (agreed at the last one)
     Layout *h_layout = nullptr;  // pinned, one per rank (all-gathered at every binning)
     uint32_t *d_layout = nullptr;
     // peer mapping (cudaIpc): neighbours' state buffers, every rank's mailbox
@@ -764,6 +765,7 @@ int shard_grid_fitted(Shard *s, fp_flock *f) {
     s->own0 = 0;
     s->own_n = n_own;
     s->n_all = n_own;
+    s->next_fits = true;  // `need` above covers the first binning's sort input on every rank
     f->bin_valid = false;
 
     // grid scratch for the largest array a binning can sort
@@ -803,6 +805,33 @@ int shard_grid_fitted(Shard *s, fp_flock *f) {
     return ipc_setup(s, f);
 }
 
+// A failure decided on one rank in the middle of a collective protocol must become every rank's
+// failure before anybody stops talking (NCCL has no time-out: the peers would wait for ever).
+// Max-all-reduce of one word, read back; ~40 us.
+static int slab_vote(Shard *s, fp_flock *f, uint32_t mine, uint32_t *any) {
+    s->h_live[10] = mine;
+    uint32_t *d = s->d_layout;
+    FP_CUDA(cudaMemcpyAsync(d, s->h_live + 10, sizeof(uint32_t), cudaMemcpyHostToDevice, f->stream));
+    FP_NCCL(s, s->api.AllReduce(d, d, 1, ncclUint32, ncclMax, s->comm, f->stream));
+    FP_CUDA(cudaMemcpyAsync(s->h_live + 11, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, f->stream));
+    FP_CUDA(cudaStreamSynchronize(f->stream));
+    *any = s->h_live[11];
+    return FP_OK;
+}
+static int slab_capacity_error(fp_flock *f, const char *what) {
+    // (every rank takes this exit together; the status bit tells a caller polling fp_flock_status)
+    const unsigned bit = FP_STATUS_SLAB_CAPACITY;
+    unsigned cur = 0;
+    cudaMemcpyAsync(&cur, f->d_status, sizeof(cur), cudaMemcpyDeviceToHost, f->stream);
+    cudaStreamSynchronize(f->stream);
+    cur |= bit;
+    cudaMemcpyAsync(f->d_status, &cur, sizeof(cur), cudaMemcpyHostToDevice, f->stream);
+    cudaStreamSynchronize(f->stream);
+    set_error(std::string("slab capacity exceeded on some rank (") + what +
+              "): the flock is too clustered for this many ranks");
+    return FP_ERR_UNSUPPORTED;
+}
+
 // ---- a binning of the slab ------------------------------------------------------------------
 // in:  owned records in f->pos[cur][own0 .. own0 + own_n) (any order).  Collective; the caller
 // has settled.  out: [ghost L | owned | ghost R] cell-sorted in the other buffer, which becomes
@@ -812,9 +841,12 @@ static int slab_rebin(Shard *s, fp_flock *f) {
     GridWork &w = f->work;
     const uint32_t n = s->own_n, mc = s->mig_cap;
     const uint32_t m = n + 2 * (mc + 1);
+    // (whether this binning's sort input fits was agreed by all ranks at the previous binning, or is
+    // guaranteed by the sizing of a fresh fit: nobody leaves the protocol alone)
+    if (!s->next_fits) return slab_capacity_error(f, "sort input");
     if ((uint64_t)s->own0 + m > f->cap) {
-        set_error("slab capacity exceeded (flock too clustered for this many ranks)");
-        return FP_ERR_UNSUPPORTED;
+        set_error("internal: slab sort input exceeds the buffers although every rank agreed it fits");
+        return FP_ERR_INVALID;
     }
     const bool has[2] = {s->rank > 0, s->rank < s->world - 1};
     const int nbr[2] = {s->rank - 1, s->rank + 1};
@@ -883,9 +915,11 @@ static int slab_rebin(Shard *s, fp_flock *f) {
     FP_CUDA(cudaEventSynchronize(s->ev_live));
     const uint32_t nL = s->h_live[0], f_end = s->h_live[1], l_beg = s->h_live[2], o_end = s->h_live[3],
                    n_all = s->h_live[4];
-    if (n_all > f->cap || o_end < nL || n_all < o_end) {
-        set_error("slab capacity exceeded (ghost layers do not fit)");
-        return FP_ERR_UNSUPPORTED;
+    {
+        uint32_t any = 0;
+        const uint32_t mine = (n_all > f->cap || o_end < nL || n_all < o_end) ? 1u : 0u;
+        if ((rc = slab_vote(s, f, mine, &any))) return rc;
+        if (any) return slab_capacity_error(f, "ghost layers");
     }
     // 5. boundary layers -> the neighbours' ghost blocks, verbatim (same order on both sides)
     const uint32_t sb[2] = {nL, l_beg}, se[2] = {std::min(f_end, o_end), o_end};  // what I send: first / last layer
@@ -907,7 +941,9 @@ static int slab_rebin(Shard *s, fp_flock *f) {
     // 6. every rank learns every layout (where my boundary layers land in the neighbours' arrays)
     f->cur ^= 1;
     w.soa_cur ^= 1;
-    Shard::Layout me{nL, o_end - nL, n_all - o_end, (uint32_t)f->cur, (uint32_t)w.soa_cur, {0, 0, 0}};
+    // does the NEXT binning's sort input ([ghost L | owned | two receive regions]) fit my buffers?
+    const uint32_t fits = (uint64_t)nL + (o_end - nL) + 2ull * (mc + 1) <= f->cap ? 1u : 0u;
+    Shard::Layout me{nL, o_end - nL, n_all - o_end, (uint32_t)f->cur, (uint32_t)w.soa_cur, fits, {0, 0}};
     constexpr size_t LW = sizeof(Shard::Layout) / 4;
     s->h_layout[s->rank] = me;
     FP_CUDA(cudaMemcpyAsync(s->d_layout + LW * s->rank, &s->h_layout[s->rank], sizeof(me), cudaMemcpyHostToDevice,
@@ -915,6 +951,8 @@ static int slab_rebin(Shard *s, fp_flock *f) {
     FP_NCCL(s, s->api.AllGather(s->d_layout + LW * s->rank, s->d_layout, LW, ncclUint32, s->comm, f->stream));
     FP_CUDA(cudaMemcpyAsync(s->h_layout, s->d_layout, sizeof(me) * s->world, cudaMemcpyDeviceToHost, f->stream));
     FP_CUDA(cudaStreamSynchronize(f->stream));
+    s->next_fits = true;
+    for (int q = 0; q < s->world; ++q) s->next_fits = s->next_fits && s->h_layout[q].next_fits != 0;
     w.home = w.keys[buf];
     s->own0 = nL;
     s->own_n = o_end - nL;
@@ -1019,9 +1057,10 @@ static int slab_steps(Shard *s, fp_flock *f, uint32_t nsteps) {
         if (f->pending.size() >= 256 && (rc = shard_settle(s, f))) return rc;
         if ((rc = ensure_slab(s, f))) return rc;
         if ((!f->bin_valid || f->plan_left <= 0) && (rc = shard_settle(s, f))) return rc;
-        flock_select_leads(f);
+        const uint32_t lead_ver = flock_select_leads(f);
         if ((rc = flock_mark(f))) return rc;
-        f->pending.push_back({f->ordinal, f->cur, w.soa_cur, f->table_cursor, f->steps_since_fit, f->steps_since_bin});
+        f->pending.push_back({f->ordinal, f->cur, w.soa_cur, f->table_cursor, f->steps_since_fit, f->steps_since_bin,
+                              lead_ver});
         if (!f->bin_valid || f->plan_left <= 0) {
             if ((rc = slab_rebin(s, f))) return rc;
         } else if ((rc = launch_skin_gate(f->stream, w.ctl, f->ordinal, 0, f->P.dt, f->skin_budget,
@@ -1029,7 +1068,7 @@ static int slab_steps(Shard *s, fp_flock *f, uint32_t nsteps) {
                                           f->d_status))) {
             return rc;
         }
-        if ((rc = flock_nl_prepare(f, s->lgrid, slab_walk_io(s, f, true)))) return rc;  // (experimental; no-op by default)
+        if ((rc = flock_nl_prepare(f, s->lgrid, slab_walk_io(s, f, true)))) return rc;
         if ((rc = flock_mark(f))) return rc;
         if ((rc = flock_step_walk(f, s->lgrid, slab_walk_io(s, f, true)))) return rc;
         if ((rc = slab_post(s, f))) return rc;
@@ -1076,6 +1115,12 @@ int shard_settle(Shard *s, fp_flock *f) {
         }
         const fp_flock::Pending at = f->pending[k];
         const uint32_t redo = (uint32_t)(f->pending.size() - k);
+        {   // versions of the steps to redo, ahead of whatever an enclosing replay still has to enqueue
+            std::vector<uint32_t> vers;
+            for (size_t q = k; q < f->pending.size(); ++q) vers.push_back(f->pending[q].lead_ver);
+            vers.insert(vers.end(), f->replay_lead_vers.begin(), f->replay_lead_vers.end());
+            f->replay_lead_vers.swap(vers);
+        }
         f->pending.clear();
         f->cur = at.cur;
         f->work.soa_cur = at.soa_cur;
@@ -1157,12 +1202,15 @@ int shard_tap(Shard *s, fp_flock *f, int tap, const TapOut &out) {
         // a tap bins the flock where it stands (collective), then walks the owned slots
         if ((rc = ensure_slab(s, f))) return rc;
         if ((rc = slab_rebin(s, f))) return rc;
-        rc = launch_grid_walk(f->stream, f->P, s->lgrid, tap, slab_walk_io(s, f, false), f->d_status, out);
-        if (rc) return rc;
+        if ((rc = flock_tap_walk(f, s->lgrid, tap, slab_walk_io(s, f, false), out))) return rc;
     } else {
         if ((rc = allpairs_prepare(s, f))) return rc;
+        if (f->P.numerics_fast &&
+            (rc = launch_bounds(f->stream, s->all_pos[s->acur], nullptr, (uint32_t)s->n_global, f->d_bounds)))
+            return rc;
         rc = launch_allpairs(f->stream, f->P, tap, s->all_pos[s->acur], s->all_vel[s->acur],
-                             (uint32_t)s->n_global, s->first, s->n_slice, nullptr, nullptr, f->d_status, out);
+                             (uint32_t)s->n_global, s->first, s->n_slice, nullptr, nullptr, f->d_status, out, 0,
+                             f->d_bounds);
         if (rc) return rc;
     }
     return reduce_tap(s, f, tap, out);
@@ -1234,6 +1282,58 @@ int shard_read_local(Shard *s, fp_flock *f, uint64_t *n_local, uint64_t *out_ind
                             f->stream));
     FP_CUDA(cudaMemcpyAsync(out_aos6, d_aos, (size_t)own * 6 * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
     FP_CUDA(cudaStreamSynchronize(f->stream));
+    return FP_OK;
+}
+
+// rows k of (idx, aos6) -> records first + k; a row whose index differs from the record's flags 64
+__global__ void local_write_kernel(float4 *__restrict__ pos, float4 *__restrict__ vel, uint32_t n,
+                                   const unsigned long long *__restrict__ idx, const float *__restrict__ aos6,
+                                   unsigned *__restrict__ status) {
+    const uint32_t i = blockIdx.x * SB + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos[i];
+    if ((unsigned long long)__float_as_uint(p.w) != idx[i]) {
+        atomicOr(status, 64u);
+        return;
+    }
+    const float *s = aos6 + 6ull * i;
+    pos[i] = make_float4(s[0], s[1], s[2], p.w);
+    vel[i] = make_float4(s[3], s[4], s[5], 0.0f);
+}
+
+int shard_write_local(Shard *s, fp_flock *f, uint64_t n_local, const uint64_t *index, const float *aos6) {
+    int rc = shard_settle(s, f);
+    if (rc) return rc;
+    const uint32_t first = s->rep == REP_SLAB ? s->own0 : 0u;
+    const uint32_t n = s->rep == REP_SLAB ? s->own_n : f->n;
+    if (n_local != n) {
+        set_error("write_local: the row count differs from what fp_flock_read_local lists");
+        return FP_ERR_INVALID;
+    }
+    if (!n) return FP_OK;
+    if (!index || !aos6) {
+        set_error("null input");
+        return FP_ERR_INVALID;
+    }
+    const size_t bytes = (size_t)n * (6 * sizeof(float) + sizeof(unsigned long long));
+    if (bytes > f->stage_bytes) {
+        if (f->d_stage) cudaFree(f->d_stage);
+        f->d_stage = nullptr;
+        f->stage_bytes = 0;
+        FP_CUDA(cudaMalloc(&f->d_stage, bytes));
+        f->stage_bytes = bytes;
+    }
+    unsigned long long *d_idx = (unsigned long long *)f->d_stage;
+    float *d_aos = (float *)(d_idx + n);
+    FP_CUDA(cudaMemcpyAsync(d_idx, index, (size_t)n * sizeof(unsigned long long), cudaMemcpyHostToDevice, f->stream));
+    FP_CUDA(cudaMemcpyAsync(d_aos, aos6, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+    local_write_kernel<<<nblk(n), SB, 0, f->stream>>>(f->pos[f->cur] + first, f->vel[f->cur] + first, n, d_idx, d_aos,
+                                                     f->d_status);
+    count_launch();
+    FP_CUDA(cudaGetLastError());
+    FP_CUDA(cudaStreamSynchronize(f->stream));  // the caller's buffers are not retained
+    f->bin_valid = false;      // positions moved outside the walk's displacement accounting
+    s->global_valid = false;
     return FP_OK;
 }
 

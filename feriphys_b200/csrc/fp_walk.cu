@@ -340,23 +340,13 @@ static int launch3(cudaStream_t st, const DevParams &P, const GridDesc &g, const
     return FP_OK;
 }
 
-int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, int variant,
-                      const WalkIO &io, unsigned *status, const TapOut &tap_out) {
-#define FP_W3(B, T, C)                                                          \
-    return tap == TAP_STEP ? launch3<TAP_STEP, B, T, C>(st, P, g, io, status, tap_out) \
-                           : launch3<TAP_ACCEL, B, T, C>(st, P, g, io, status, tap_out)
-    switch (variant) {
-        case 31: FP_W3(128, 1904, 64);   // 43.6 KB: still 5 CTAs / SM, and the tile overflows ~never
-        case 38: FP_W3(128, 1792, 64);   // 42.2 KB
-        case 32: FP_W3(128, 1792, 40);   // 37 KB: 6 CTAs / SM
-        case 33: FP_W3(128, 1792, 56);   // 41 KB: 5 CTAs / SM
-        case 34: FP_W3(128, 1792, 48);   // 39 KB: 5 CTAs / SM
-        case 35: FP_W3(128, 1792, 80);   // 47 KB: 4 CTAs / SM
-        case 36: FP_W3(128, 1536, 64);   // 40 KB: 5 CTAs / SM
-        case 37: FP_W3(64, 1024, 64);    // 23 KB: 9 CTAs / SM
-        default: FP_W3(128, 1904, 64);   // one drain per boid almost always: lists average 17 entries
-    }
-#undef FP_W3
+int launch_grid_walk3(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, const WalkIO &io,
+                      unsigned *status, const TapOut &tap_out) {
+    // 128 boids, a tile of 1904 candidates, 64-entry survivor lists: 43.6 KB, five CTAs per SM; the
+    // tile overflows ~never at the densities lists are built for, and one drain per boid almost
+    // always (lists average 17 entries).  Other shapes were measured and lost.
+    return tap == TAP_STEP ? launch3<TAP_STEP, 128, 1904, 64>(st, P, g, io, status, tap_out)
+                           : launch3<TAP_ACCEL, 128, 1904, 64>(st, P, g, io, status, tap_out);
 }
 
 }  // namespace fp

@@ -1,46 +1,47 @@
-// fp_walk_nl.cu -- K3 with standing candidate lists (EXPERIMENTAL, TAP_STEP only, not the
-// default: FP_WALK_VARIANT=41 .. 46, see nl_prepare in fp_api.cu).  The plain form (41) has run on
-// a B200: bit-identical to the production walk in every run compared, C4 5.66 -> 3.85 ms/step
-// (profiles/r1_nl_*.log); the other forms are written but have not run yet.
+// fp_walk_nl.cu -- K3 on standing candidate lists: the grid step's default form.
 //
-// With lazy re-binning a binning stands for ~20 steps, yet the production
-// walk (fp_walk.cu) pre-gates all ~160 candidates of a boid's 27 home cells in every one of
-// them -- 48 % of its instructions (profiles/r1_c4_walk_hotspots.txt) -- to find the ~34
-// that are within reach.  Here that work is done ONCE per binning:
+// With lazy re-binning a binning stands for dozens of steps, yet the plain staged
+// walk (fp_walk.cu) pre-gates all ~160 candidates of a boid's 27 home cells in every one of them
+// -- 48 % of its instructions (profiles/r1_c4_walk_hotspots.txt) -- to find the ~34 that are within
+// reach.  Here that work is done ONCE per binning:
 //
-//   nl_build_kernel  (right after a binning, positions = the binned positions)
-//       stages the same nine intervals as the production walk, keeps every candidate whose
-//       squared distance is below (reach + skin)^2 (1 + 1e-5), and writes the survivors' tile
-//       offsets (16 bit, row << 12 | offset, ascending slot order) to a per-thread list in
-//       global memory, [cta][entry][thread] so that entry k of a warp is one 64-byte run;
-//       also the per-boid count and the CTA's tile layout (nine intervals).
-//   nl_walk_kernel   (every step until the next binning)
-//       stages the tile from the cached layout (no cell-table look-ups, no reductions), runs
-//       the production pre-gate -- fused squared distance against m2_cut_hi and the
-//       conservative FOV test -- over the ~34 cached entries instead of ~160 candidates, and
-//       drains the survivors exactly as the production kernel does.
+//   nl_build_kernel  (after a binning)
+//       stages the same nine intervals as the plain walk, keeps every candidate whose squared
+//       distance is below (reach + skin)^2 (1 + 1e-5), and writes the survivors' tile offsets
+//       (16 bit, row << 12 | offset, ascending slot order, the boid itself left out) to a
+//       per-thread list in global memory, [cta][entry][thread] so that entry k of a warp is one
+//       64-byte run; also the per-boid count and the CTA's tile layout (nine intervals).
+//   nl_walk_kernel   (EXACT numerics: every step until the next binning)
+//       stages the tile from the cached layout (no cell-table look-ups, no reductions), runs the
+//       plain walk's fused pre-gate over the ~34 cached entries instead of ~160 candidates, and
+//       drains the survivors exactly as the plain walk does: bit-identical to it.
+//   nl_fast_kernel   (FAST numerics, fp_flock_set_numerics)
+//       one pass over the cached entries with positions AND velocities staged in shared memory:
+//       exact squared distance (so the distance decisions are the reference's), the field-of-view
+//       decision on a fused cosine outside a 1e-5 guard band and by the exact sequence inside it,
+//       forces with FMA and MUFU.RSQ.  Neighbour sets are bit-exact, accelerations agree with the
+//       reference to ~1e-6 relative (bar: 1e-5); the summation order is still the list order.
 //
-// Exactness.  While the binning stands every boid is within skin / 2 of where it was binned
-// (the device-checked displacement bound D), so a pair closer than reach now was closer than
-// reach + skin then: the cached list is a superset of every pair the production pre-gate
-// keeps, in the same order.  The survivor list the drain sees is therefore the same list,
-// and the result is bit-identical to the production kernel's (and to the oracle's on the
-// standing listing).
+// Exactness of the lists.  While the binning stands every boid is within skin / 2 of where it was
+// binned (the device-checked displacement bound D), so a pair closer than reach now was closer
+// than reach + skin then: the cached list is a superset of every pair that can contribute, in
+// slot order.
 //
 // Capacity.  A list holds nl.vcap entries.  A CTA in which some boid has more, or whose nine
 // intervals do not fit the tile, is marked in its layout record and walks the 27 cells from
-// global memory every step (the production kernel's own path for CTAs that overflow the tile):
-// slower, same result, no effect on any other CTA.  The build counts such CTAs; the host turns
-// the lists off when they stop being rare.
+// global memory every step (the plain walk's own path for CTAs that overflow the tile): slower,
+// same result, no effect on any other CTA.  The build counts such CTAs; the host turns the lists
+// off when they stop being rare.
 #include "fp_walk_stage.cuh"
 
 namespace fp {
 
 namespace {
 
-constexpr int NL_BLOCK = 128;   // threads (= boids) per CTA, as the production walk
-constexpr int NL_TILE = 1904;   // staged candidates per CTA, as the production walk
-constexpr int NL_CAP = 64;      // survivor list (shared memory), as the production walk
+constexpr int NL_BLOCK = 128;   // threads (= boids) per CTA, as the plain walk
+constexpr int NL_TILE = 1904;   // staged candidates per CTA (build and exact walk), as the plain walk
+constexpr int NL_CAP = 48;      // survivor list of the exact walk (shared memory): six CTAs per SM
+constexpr int NF_TILE = 1568;   // staged candidates per CTA of the fast walk (positions + velocities)
 constexpr int NL_CTA_WORDS = 20;  // cached tile layout per CTA: ub[9], ue[9], [18] = no lists, 1 spare
 
 // this CTA gets no lists: it walks from global memory every step (counted once per CTA)
@@ -49,11 +50,13 @@ __device__ __forceinline__ void nl_no_lists(const NlIO &nl, uint32_t *tab) {
 }
 
 // Lays the nine CTA-wide intervals (ub, ue: multiples of 4, empty = 0, 0) out in the tile and
-// issues their bulk copies.  Called by warp 0; lane r = row r.  Returns the tile total.
+// issues their bulk copies (positions; velocities too when `tv` is given).  Called by warp 0;
+// lane r = row r.  Returns the tile total.
 template <class Smem>
 __device__ __forceinline__ uint32_t nl_stage(Smem &S, uint32_t tid, uint32_t ub, uint32_t ue,
                                              const float *__restrict__ sx, const float *__restrict__ sy,
-                                             const float *__restrict__ sz, uint32_t tile_cap) {
+                                             const float *__restrict__ sz, uint32_t tile_cap,
+                                             float4 *tv = nullptr, const float4 *__restrict__ vel_s = nullptr) {
     const uint32_t len = ue - ub;
     uint32_t inc = len;  // inclusive prefix sum over the lanes
 #pragma unroll
@@ -69,15 +72,43 @@ __device__ __forceinline__ uint32_t nl_stage(Smem &S, uint32_t tid, uint32_t ub,
     const bool staged = total > 0 && total <= tile_cap;
     if (tid == 0) {
         S.toff[9] = total;
-        if (staged) mbar_expect_tx(&S.bar, total * 12u);
+        if (staged) mbar_expect_tx(&S.bar, total * (tv ? 28u : 12u));
     }
     __syncwarp();
     if (staged && tid < 9 && len) {
         bulk_g2s(&S.tx[toff], sx + ub, len * 4u, &S.bar);
         bulk_g2s(&S.ty[toff], sy + ub, len * 4u, &S.bar);
         bulk_g2s(&S.tz[toff], sz + ub, len * 4u, &S.bar);
+        if (tv) bulk_g2s(tv + toff, vel_s + ub, len * 16u, &S.bar);
     }
     return total;
+}
+
+// the 27 home cells from global memory, exact pair function: a CTA without lists
+__device__ __forceinline__ V3 nl_walk_global(const DevParams &P, const GridDesc &g, const WalkIO &io, uint32_t s,
+                                             const Self &self) {
+    V3 acc = v3zero();
+    int cx, cy, cz;
+    home_cell(g, __ldg(io.home + (s - io.first)), cx, cy, cz);
+    const int z0 = max(cz - g.zspan, 0), z1 = min(cz + g.zspan, g.dim[2] - 1);
+    for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x) {
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
+            const uint32_t rowbase = row_base(g, x, y);
+            const uint32_t b = __ldg(io.cell_start + rowbase + z0);
+            const uint32_t e = __ldg(io.cell_start + rowbase + z1 + 1);
+            for (uint32_t j = b; j < e; ++j) {
+                if (j == s) continue;
+                const float4 pj = __ldg(io.pos_s + j);
+                V3 d;
+                const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
+                if (m2 >= P.m2_cut) continue;
+                const float4 vj = __ldg(io.vel_s + j);
+                V3 contrib;
+                if (pair_flock(P, self, d, m2, v3(vj.x, vj.y, vj.z), contrib)) acc = vadd(acc, contrib);
+            }
+        }
+    }
+    return acc;
 }
 
 struct NlBuildSmem {
@@ -87,21 +118,7 @@ struct NlBuildSmem {
     uint32_t toff[10], tslot[9];
     alignas(8) uint64_t bar;
 };
-constexpr int NL_STAGE_ROWS = 96;  // STAGED: rows of the shared-memory staging block (>= vcap)
 
-// STAGED = false: every entry goes straight to global memory -- a warp's 32 lanes are at 32
-// different list positions, so each 2-byte store touches its own sector (the form checked on
-// hardware, FP_WALK_VARIANT=41: a build costs 4.9 ms at C4).  STAGED = true (variant 43, not yet
-// run on hardware): entries are collected in shared memory, [entry][thread], and the CTA's
-// block is written row by row, 256 contiguous bytes per row.
-// SORTED (needs STAGED; variant 45, not yet run on hardware): the CTA's 128 boids are handed to its
-// threads in descending order of the work they will cost the walk, so that the lanes of a warp
-// finish together (unsorted, a warp runs as long as its longest gate list, ~44 entries against 34
-// on average, and its longest drain list, ~24 against 16).  Lane l of the CTA then holds boid (count[cta * 128 + l] >> 8) of the
-// CTA's slot window, with its list in column l; the count stays in the low byte.  Any
-// assignment of boids to threads gives the same result: each boid still sums its own
-// contributions in slot order.
-template <bool STAGED, bool SORTED>
 __global__ void __launch_bounds__(NL_BLOCK)
 nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     // (No look at ctl->stale: the lists describe the binning, which stands whether or not the
@@ -123,19 +140,9 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     float4 pi4 = make_float4(0, 0, 0, 0);
     bool work = false;
     int cx = 0, cy = 0, cz = 0;
-    float2 vhx = make_float2(0, 0), vhy = vhx, vhz = vhx;  // SORTED: direction of flight, both halves
     if (active) {
         pi4 = io.pos_s[s];
-        if (SORTED) {
-            const float4 vi4 = io.vel_s[s];
-            work = __float_as_uint(vi4.w) == 0u;
-            const float inv = rsqrtf(fmaf(vi4.z, vi4.z, fmaf(vi4.y, vi4.y, vi4.x * vi4.x)));  // a prediction: no need to be exact
-            vhx = make_float2(vi4.x * inv, vi4.x * inv);
-            vhy = make_float2(vi4.y * inv, vi4.y * inv);
-            vhz = make_float2(vi4.z * inv, vi4.z * inv);
-        } else {
-            work = __float_as_uint(io.vel_s[s].w) == 0u;  // not a ghost record
-        }
+        work = __float_as_uint(io.vel_s[s].w) == 0u;  // not a ghost record
         home_cell(g, __ldg(io.home + (s - io.first)), cx, cy, cz);
     }
     // the nine slot ranges of this boid, rows in ascending key order (dx outer, dy inner)
@@ -176,14 +183,14 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
         if (tid < 9) {
             S.ub[tid] = ub;
             S.ue[tid] = ue;
-            tab[tid] = ub;       // the layout every nl_walk_kernel launch of this binning re-uses
+            tab[tid] = ub;       // the layout every walk launch of this binning re-uses
             tab[9 + tid] = ue;
         }
-        nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], NL_TILE);
+        nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], nl.tile_cap);
     }
     __syncthreads();
     const uint32_t total = S.toff[9];
-    if (total > (uint32_t)NL_TILE) {  // dense cluster: the tile does not fit -- no lists for this CTA
+    if (total > nl.tile_cap) {  // dense cluster: the tile does not fit -- no lists for this CTA
         if (tid == 0) nl_no_lists(nl, tab);
         return;
     }
@@ -196,14 +203,8 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     const uint32_t t_self = work ? s - S.tslot[4] : 0xffffu;  // tile offset of the boid itself (row 4)
     if (total > 0) mbar_wait(&S.bar, 0);
     uint16_t *const out = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + tid;  // entry k at out[k * BLOCK]
-    uint16_t *const stg = reinterpret_cast<uint16_t *>(smem_raw + sizeof(NlBuildSmem)) + tid;  // STAGED: same layout
-    const uint32_t vcap = STAGED ? min(nl.vcap, (uint32_t)NL_STAGE_ROWS) : nl.vcap;
+    const uint32_t vcap = nl.vcap;
     uint32_t w = 0;  // entries found
-    uint32_t pred = 0;  // SORTED: entries that would pass the walk's pre-gate as things stand now
-    // (what that takes of DevParams -- m2_cut_hi, fov_kh, fov_kl -- sits behind the counter in nl.flag)
-    const float sp_cut = SORTED ? __uint_as_float(__ldg(nl.flag + 1)) : 0.0f;
-    const float sp_kh = SORTED ? __uint_as_float(__ldg(nl.flag + 2)) : 0.0f;
-    const float sp_kl = SORTED ? __uint_as_float(__ldg(nl.flag + 3)) : 0.0f;
     const float2 nsx = make_float2(-pi4.x, -pi4.x), nsy = make_float2(-pi4.y, -pi4.y),
                  nsz = make_float2(-pi4.z, -pi4.z);
 #pragma unroll 1
@@ -211,7 +212,7 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
         const uint32_t pk = S.rng[r][tid];
         const uint32_t t0 = pk & 0xffffu, len = pk >> 16;
         const uint32_t tag = (uint32_t)r << 12;
-        // four candidates at an even tile index per batch, packed FP32 (as the production pre-gate);
+        // four candidates at an even tile index per batch, packed FP32 (as the plain walk's pre-gate);
         // the fused sum of squares is within 4e-7 relative of the exact one, the cut carries 1e-5
         auto gate4 = [&](uint32_t T, uint32_t live) {
             const float2 x01 = *reinterpret_cast<const float2 *>(&S.tx[T]);
@@ -226,19 +227,11 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
             const float2 m01 = __ffma2_rn(dz01, dz01, __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01)));
             const float2 m23 = __ffma2_rn(dz23, dz23, __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23)));
             const float mm[4] = {m01.x, m01.y, m23.x, m23.y};
-            float ss[4] = {0, 0, 0, 0};
-            if (SORTED) {  // the walk's conservative FOV test (fp_walk.cu), for the prediction
-                const float2 q01 = __ffma2_rn(vhz, dz01, __ffma2_rn(vhy, dy01, __fmul2_rn(vhx, dx01)));
-                const float2 q23 = __ffma2_rn(vhz, dz23, __ffma2_rn(vhy, dy23, __fmul2_rn(vhx, dx23)));
-                ss[0] = q01.x * fabsf(q01.x); ss[1] = q01.y * fabsf(q01.y);
-                ss[2] = q23.x * fabsf(q23.x); ss[3] = q23.y * fabsf(q23.y);
-            }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if ((live >> u & 1u) && !(mm[u] >= nl.m2_wide) && T + u != t_self) {  // NaN never drops
-                    if (w < vcap) (STAGED ? stg : out)[(size_t)w * NL_BLOCK] = (uint16_t)(tag | (T + u));
+                    if (w < vcap) out[(size_t)w * NL_BLOCK] = (uint16_t)(tag | (T + u));
                     ++w;
-                    if (SORTED && !(mm[u] >= sp_cut) && !(ss[u] < sp_kh * mm[u] && ss[u] > sp_kl * mm[u])) ++pred;
                 }
         };
         if (len) {
@@ -252,90 +245,28 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
             if (T < B) gate4(T, (1u << (B - T)) - 1u);
         }
     }
-    if (!SORTED && active) nl.count[s - io.first] = (uint16_t)min(w, vcap);
+    if (active) nl.count[s - io.first] = (uint16_t)min(w, vcap);
     if (__any_sync(0xffffffffu, w > vcap) && (tid & 31) == 0) nl_no_lists(nl, tab);
-    if (STAGED && SORTED) {
-        static_assert(!SORTED || STAGED, "the sorted layout is written from the staging block");
-        // Sort key: the work a boid will cost the walk -- mostly its drain (entries that survive the
-        // pre-gate: predicted from the velocities of this moment, the field of view turns slowly),
-        // a little its gate (all entries).  Emulated on a C3-density flock: sorting by
-        // this key takes ~14 % off the gate + drain work of a warp, by the list length alone 9 %.
-        constexpr int NKEY = 128;
-        __shared__ uint32_t hist[NKEY];  // threads per key, then running ranks
-        __shared__ uint32_t wmax_s;
-        const uint32_t c = min(w, vcap);
-        const uint32_t key = min(pred + c / 4u, (uint32_t)NKEY - 1u);
-        hist[tid] = 0u;  // (NKEY == NL_BLOCK)
-        if (tid == 0) wmax_s = 0u;
-        __syncthreads();
-        atomicAdd(&hist[key], 1u);
-        atomicMax(&wmax_s, c);
-        __syncthreads();
-        if (tid < 32) {  // first rank of each key, costliest first: lane l owns keys 127 - 4 l .. 124 - 4 l
-            uint32_t t[4], sum = 0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                t[u] = hist[NKEY - 1 - (4 * tid + u)];
-                sum += t[u];
-            }
-            uint32_t inc = sum;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
-                if ((int)tid >= off) inc += o;
-            }
-            uint32_t run = inc - sum;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                hist[NKEY - 1 - (4 * tid + u)] = run;
-                run += t[u];
-            }
-        }
-        __syncthreads();
-        const uint32_t rank = atomicAdd(&hist[key], 1u);  // (order within one key: whoever comes first)
-        nl.count[(size_t)blockIdx.x * NL_BLOCK + rank] = (uint16_t)(c | (tid << 8));
-        uint16_t *const col = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + rank;
-        const uint32_t rows = wmax_s;
-        for (uint32_t k = 0; k < rows; ++k) col[(size_t)k * NL_BLOCK] = stg[(size_t)k * NL_BLOCK];
-    } else if (STAGED) {
-        // rows 0 .. (longest list of the CTA) of the staging block, as they are: a thread's entries
-        // past its own count are whatever the shared memory held, and are never read as entries
-        __shared__ uint32_t wmax;  // longest list of the CTA
-        if (tid == 0) wmax = 0u;
-        __syncthreads();
-        const uint32_t wm = __reduce_max_sync(0xffffffffu, min(w, vcap));
-        if ((tid & 31) == 0) atomicMax(&wmax, wm);
-        __syncthreads();
-        const uint32_t rows = wmax;
-        for (uint32_t k = 0; k < rows; ++k) out[(size_t)k * NL_BLOCK] = stg[(size_t)k * NL_BLOCK];
-    }
 }
 
-template <int CAP>
 struct NlWalkSmem {
     alignas(16) float tx[NL_TILE + 8], ty[NL_TILE + 8], tz[NL_TILE + 8];
-    uint16_t list[CAP][NL_BLOCK];  // per-thread survivor lists: tile offsets
+    uint16_t list[NL_CAP][NL_BLOCK];  // per-thread survivor lists: tile offsets
     uint32_t toff[10], tslot[9];
     alignas(8) uint64_t bar;
 };
 
-// <CAP, CTAS>: survivor-list capacity and the CTAs per SM the registers are budgeted for.
-// <64, 5> is the form checked on hardware (39 KB of shared memory: five CTAs per SM, 102
-// registers).  <48, 6> (variant 44, not yet run): 35 KB, six CTAs per SM at 80 registers -- with
-// ~17 survivors per boid a 48-entry list still drains once per boid almost always.
-template <int CAP, int CTAS, bool SORTED>
-__global__ void __launch_bounds__(NL_BLOCK, CTAS)
+// EXACT numerics: 35 KB of shared memory, six CTAs per SM at 80 registers.  With ~17 survivors per
+// boid a 48-entry list drains once per boid almost always (measured against 64 entries at five
+// CTAs per SM: C4 3.34 against 3.55 ms, profiles/r2_bench_*).
+__global__ void __launch_bounds__(NL_BLOCK, 6)
 nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO nl, unsigned *__restrict__ status) {
     if (io.ctl && io.ctl->stale) return;  // lazy re-binning: this step is void
     const float4 *__restrict__ vel_s = io.vel_s;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    NlWalkSmem<CAP> &S = *reinterpret_cast<NlWalkSmem<CAP> *>(smem_raw);
+    NlWalkSmem &S = *reinterpret_cast<NlWalkSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
-    // SORTED: which boid of the CTA's window this thread holds, and its count, come packed from the build
-    // (a CTA without lists keeps the plain assignment: its build may not have got as far as the ranking)
-    const bool ranked = SORTED && !__ldg(nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS + 18);
-    const uint32_t packed = ranked ? __ldg(nl.count + (size_t)blockIdx.x * NL_BLOCK + tid) : 0u;
-    const uint32_t s = io.first + blockIdx.x * NL_BLOCK + (ranked ? packed >> 8 : tid);
+    const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
     const bool active = s < io.last;
     if (tid == 0) mbar_init(&S.bar, 1);
 
@@ -344,7 +275,7 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     if (active) {
         pi4 = io.pos_s[s];
         vi4 = vel_s[s];
-        n_c = ranked ? (packed & 0xffu) : __ldg(nl.count + (s - io.first));
+        n_c = __ldg(nl.count + (s - io.first));
     }
     // this CTA's list block and the first batch of entries, in flight while the tile is staged
     const uint16_t *const vlp = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + tid;
@@ -363,30 +294,8 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     const uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
     V3 acc = v3zero();
     if (__ldg(tab + 18)) {
-        // a CTA without lists (tile or list overflow at build time): the one-phase walk of the 27
-        // home cells from global memory, as the production kernel does for its overflowing CTAs
-        if (work) {
-            int cx, cy, cz;
-            home_cell(g, __ldg(io.home + (s - io.first)), cx, cy, cz);
-            const int z0 = max(cz - g.zspan, 0), z1 = min(cz + g.zspan, g.dim[2] - 1);
-            for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dim[0] - 1); ++x) {
-                for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dim[1] - 1); ++y) {
-                    const uint32_t rowbase = row_base(g, x, y);
-                    const uint32_t b = __ldg(io.cell_start + rowbase + z0);
-                    const uint32_t e = __ldg(io.cell_start + rowbase + z1 + 1);
-                    for (uint32_t j = b; j < e; ++j) {
-                        if (j == s) continue;
-                        const float4 pj = __ldg(io.pos_s + j);
-                        V3 d;
-                        const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
-                        if (m2 >= P.m2_cut) continue;
-                        const float4 vj = __ldg(vel_s + j);
-                        V3 contrib;
-                        if (pair_flock(P, self, d, m2, v3(vj.x, vj.y, vj.z), contrib)) acc = vadd(acc, contrib);
-                    }
-                }
-            }
-        }
+        // a CTA without lists (tile or list overflow at build time)
+        if (work) acc = nl_walk_global(P, g, io, s, self);
         if (active) walk_finish<TAP_STEP>(P, s, pi4, vi4, self, acc, 0u, 0ull, io, status, TapOut{});
         return;
     }
@@ -406,12 +315,12 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     const float kh = P.fov_kh, kl = P.fov_kl;
 #pragma unroll 1
     for (;;) {
-        int room = CAP - (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);
+        int room = NL_CAP - (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);
         const bool more = base < nmax;
-        if (room < 4 || (!more && room < CAP)) {
+        if (room < 4 || (!more && room < NL_CAP)) {
             drain_list<NL_BLOCK>(P, self, lst, cnt, S.tx, S.ty, S.tz, S.tslot, t_self, vel_s, acc);
             cnt = 0;
-            room = CAP;
+            room = NL_CAP;
         }
         if (!more) break;
         const uint32_t end = min(base + ((uint32_t)room & ~3u), (nmax + 3u) & ~3u);
@@ -425,7 +334,7 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
                 e2 = __ldcs(vlp + (size_t)(k + 6) * NL_BLOCK);
                 e3 = __ldcs(vlp + (size_t)(k + 7) * NL_BLOCK);
             }
-            // The production pre-gate (fp_walk.cu), one candidate per lane-slot: fused squared
+            // The plain walk's pre-gate (fp_walk.cu), one candidate per lane-slot: fused squared
             // distance against m2_cut_hi, and the conservative FOV test KL m2 < q |q| < KH m2
             // (drops only pairs culled with a 1e-5 margin; NaN never drops).
             float mm[4], ss[4];
@@ -454,6 +363,151 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     walk_finish<TAP_STEP>(P, s, pi4, vi4, self, acc, 0u, 0ull, io, status, TapOut{});
 }
 
+// ---- FAST numerics ----------------------------------------------------------------------------
+struct NlFastSmem {
+    alignas(16) float tx[NF_TILE + 8], ty[NF_TILE + 8], tz[NF_TILE + 8];
+    alignas(16) float4 tv[NF_TILE];  // velocities of the staged candidates (.w: record flag, unused)
+    uint32_t toff[10], tslot[9];
+    alignas(8) uint64_t bar;
+};
+
+// One entry of a boid's cached list under FAST numerics.  The squared distance is the reference's
+// own (separately rounded, boid.rs:94-96 through cgmath's dot), so "in range" and "weight 1" are its
+// decisions.  The cosine of the sight angle is fused and uses MUFU.RSQ: within ~1e-6 of the
+// reference's (boid.rs:102-105); the decision is taken on it when it is further than the guard band
+// from both ends of the culled interval [-1, cstar], else `unsure` sends the pair down the exact path.
+struct FastPair {
+    float dx, dy, dz, m2, r;
+    bool pass;    // contributes, decided outside the guard bands
+    bool unsure;  // in range but degenerate or inside a guard band: the exact sequence decides
+};
+__device__ __forceinline__ FastPair fast_gate(const DevParams &P, const Self &self, float px, float py, float pz,
+                                              bool live) {
+    FastPair f;
+    f.dx = fsub(px, self.p.x);
+    f.dy = fsub(py, self.p.y);
+    f.dz = fsub(pz, self.p.z);
+    f.m2 = fadd(fadd(fmul(f.dx, f.dx), fmul(f.dy, f.dy)), fmul(f.dz, f.dz));
+    const float q = fmaf(self.vhat.z, f.dz, fmaf(self.vhat.y, f.dy, self.vhat.x * f.dx));
+    f.r = rsqrt_seed(f.m2);
+    const float c = q * f.r;
+    const float gc = (c - P.fz_a) * (c - P.fz_b);   // <= 0: culled (acosf(c) > max_sight_angle)
+    const bool in = live && !(f.m2 >= P.m2_cut);
+    // coincident positions (abs_diff_eq! guards, boid.rs:111,121), NaN, and cosines in the guard band
+    const bool clear = fabsf(gc) > P.fz_gc_tol && f.m2 >= 1e-12f;
+    f.unsure = in && !clear;
+    f.pass = in && clear && gc > 0.0f;
+    return f;
+}
+// contribution of a pair that passed, accumulated with FMAs: w_d ((av + ce) + vm)  (boid.rs:162-165)
+__device__ __forceinline__ void fast_force(const DevParams &P, const Self &self, const FastPair &f, float4 vj,
+                                           float &ax, float &ay, float &az) {
+    // dist: the seed refined to the correctly rounded square root (it enters the ramp by difference)
+    const float g0 = f.m2 * f.r, h = 0.5f * f.r;
+    const float mag = fmaf(fmaf(-g0, g0, f.m2), h, g0);
+    const float coef = fmaf(P.f_c, mag, P.neg_f_a * (f.r * f.r)) * f.r;  // ((-f_a / d^2) + f_c d) / d, on d
+    const float w = f.m2 <= P.m2_one ? 1.0f : (mag - P.thr) * P.fz_rinv_fall;  // boid.rs:152-161 (F7)
+    const float dvx = vj.x - self.v.x, dvy = vj.y - self.v.y, dvz = vj.z - self.v.z;
+    const bool vsm = fmaxf(fmaxf(fabsf(dvx), fabsf(dvy)), fabsf(dvz)) <= FP_F32_EPSILON;  // boid.rs:132
+    const float cw = coef * w, fw = vsm ? 0.0f : P.f_v * w;
+    ax = fmaf(cw, f.dx, fmaf(fw, dvx, ax));
+    ay = fmaf(cw, f.dy, fmaf(fw, dvy, ay));
+    az = fmaf(cw, f.dz, fmaf(fw, dvz, az));
+}
+
+template <int TAP>
+__global__ void __launch_bounds__(NL_BLOCK, 5)
+nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO nl, unsigned *__restrict__ status,
+               TapOut tap) {
+    if (TAP == TAP_STEP && io.ctl && io.ctl->stale) return;  // lazy re-binning: this step is void
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    NlFastSmem &S = *reinterpret_cast<NlFastSmem *>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
+    const bool active = s < io.last;
+    if (tid == 0) mbar_init(&S.bar, 1);
+
+    float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
+    uint32_t n_c = 0;
+    if (active) {
+        pi4 = io.pos_s[s];
+        vi4 = io.vel_s[s];
+        n_c = __ldg(nl.count + (s - io.first));
+    }
+    const uint16_t *const vlp = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + tid;
+    uint32_t e0 = __ldcs(vlp), e1 = __ldcs(vlp + NL_BLOCK), e2 = __ldcs(vlp + 2 * NL_BLOCK),
+             e3 = __ldcs(vlp + 3 * NL_BLOCK);
+    if (TAP == TAP_STEP && io.ctl) track_motion(io.ctl, active, pi4, vi4);
+    Self self;
+    self.p = self.v = self.vhat = v3zero();
+    bool work = false;
+    if (active) {
+        self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
+        const bool ghost = __float_as_uint(vi4.w) != 0u;
+        work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
+    }
+    if (!work) n_c = 0;
+    const uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
+    if (__ldg(tab + 18)) {  // a CTA without lists
+        V3 acc = v3zero();
+        if (work) acc = nl_walk_global(P, g, io, s, self);
+        if (active) walk_finish<TAP, true>(P, s, pi4, vi4, self, acc, 0u, 0ull, io, status, tap);
+        return;
+    }
+    __syncthreads();  // the barrier is initialised
+    if (tid < 32) {
+        const uint32_t ub = tid < 9 ? __ldg(tab + tid) : 0u, ue = tid < 9 ? __ldg(tab + 9 + tid) : 0u;
+        nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], NF_TILE, S.tv, io.vel_s);
+    }
+    __syncthreads();
+    const uint32_t nmax = __reduce_max_sync(0xffffffffu, n_c);
+    if (S.toff[9] > 0) mbar_wait(&S.bar, 0);
+
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#pragma unroll 1
+    for (uint32_t k = 0; k < nmax; k += 4) {
+        const uint32_t c[4] = {e0, e1, e2, e3};
+        if (k + 4 < nmax) {
+            e0 = __ldcs(vlp + (size_t)(k + 4) * NL_BLOCK);
+            e1 = __ldcs(vlp + (size_t)(k + 5) * NL_BLOCK);
+            e2 = __ldcs(vlp + (size_t)(k + 6) * NL_BLOCK);
+            e3 = __ldcs(vlp + (size_t)(k + 7) * NL_BLOCK);
+        }
+        FastPair f[4];
+        uint32_t t[4];
+        const uint32_t rem = n_c > k ? n_c - k : 0u;  // live entries of this batch
+        bool any_unsure = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            t[u] = c[u] & 0xfffu;  // (entries past n_c hold offsets of earlier builds: inside the arrays, unused)
+            f[u] = fast_gate(P, self, S.tx[t[u]], S.ty[t[u]], S.tz[t[u]], (uint32_t)u < rem);
+            any_unsure |= f[u].unsure;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (f[u].pass) fast_force(P, self, f[u], S.tv[t[u]], ax, ay, az);
+        if (any_unsure) {
+            // guard band / degenerate pair (rare): the reference's own sequence decides and evaluates
+#pragma unroll 1
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t tu = (u == 0 ? c[0] : u == 1 ? c[1] : u == 2 ? c[2] : c[3]) & 0xfffu;
+                const FastPair fu = fast_gate(P, self, S.tx[tu], S.ty[tu], S.tz[tu], u < rem);
+                if (!fu.unsure) continue;
+                const float4 vj = S.tv[tu];
+                V3 contrib;
+                if (pair_inrange<false>(P, self, v3(fu.dx, fu.dy, fu.dz), fu.m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar,
+                                        contrib)) {
+                    ax += contrib.x;
+                    ay += contrib.y;
+                    az += contrib.z;
+                }
+            }
+        }
+    }
+    if (!active) return;
+    walk_finish<TAP, true>(P, s, pi4, vi4, self, v3(ax, ay, az), 0u, 0ull, io, status, tap);
+}
+
 }  // namespace
 
 size_t nl_entries_elems(uint32_t rows, uint32_t vcap) {
@@ -463,51 +517,44 @@ size_t nl_entries_elems(uint32_t rows, uint32_t vcap) {
 size_t nl_cta_tab_elems(uint32_t rows) {
     return (((size_t)rows + NL_BLOCK - 1) / NL_BLOCK) * NL_CTA_WORDS;
 }
+uint32_t nl_tile_cap(bool fast) { return fast ? NF_TILE : NL_TILE; }
 
-int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl, int form,
-                    const float sort_params[3]) {
+int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl) {
     if (io.last <= io.first) return FP_OK;
     const uint32_t ctas = (io.last - io.first + NL_BLOCK - 1) / NL_BLOCK;
-    if (form & (NL_FORM_STAGED | NL_FORM_SORTED)) {
-        const int smem = (int)(sizeof(NlBuildSmem) + sizeof(uint16_t) * NL_STAGE_ROWS * NL_BLOCK);
-        if (form & NL_FORM_SORTED) {
-            // (pageable source: the copy has left the host buffer when the call returns)
-            FP_CUDA(cudaMemcpyAsync(nl.flag + 1, sort_params, 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-            FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            nl_build_kernel<true, true><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
-        } else {
-            FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            nl_build_kernel<true, false><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
-        }
-    } else {
-        const int smem = (int)sizeof(NlBuildSmem);
-        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        nl_build_kernel<false, false><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
-    }
+    const int smem = (int)sizeof(NlBuildSmem);
+    FP_CUDA(cudaFuncSetAttribute(nl_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    nl_build_kernel<<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;
 }
 
-template <int CAP, int CTAS, bool SORTED>
-static int launch_nl_walk_as(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io,
-                             const NlIO &nl, unsigned *status) {
-    const int smem = (int)sizeof(NlWalkSmem<CAP>);
-    auto kern = nl_walk_kernel<CAP, CTAS, SORTED>;
-    FP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<(io.last - io.first + NL_BLOCK - 1) / NL_BLOCK, NL_BLOCK, smem, st>>>(P, g, io, nl, status);
-    return FP_OK;
-}
-
-int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, const WalkIO &io, const NlIO &nl,
-                   unsigned *status, int form) {
+int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int tap, const WalkIO &io, const NlIO &nl,
+                   unsigned *status, const TapOut &tap_out) {
     if (io.last <= io.first) return FP_OK;
-    const bool six = form & NL_FORM_SIX_CTAS, sorted = form & NL_FORM_SORTED;
-    const int rc = six ? (sorted ? launch_nl_walk_as<48, 6, true>(st, P, g, io, nl, status)
-                                 : launch_nl_walk_as<48, 6, false>(st, P, g, io, nl, status))
-                       : (sorted ? launch_nl_walk_as<NL_CAP, 5, true>(st, P, g, io, nl, status)
-                                 : launch_nl_walk_as<NL_CAP, 5, false>(st, P, g, io, nl, status));
-    if (rc) return rc;
+    const uint32_t ctas = (io.last - io.first + NL_BLOCK - 1) / NL_BLOCK;
+    if (P.numerics_fast) {
+        const int smem = (int)sizeof(NlFastSmem);
+        if (tap == TAP_STEP) {
+            FP_CUDA(cudaFuncSetAttribute(nl_fast_kernel<TAP_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            nl_fast_kernel<TAP_STEP><<<ctas, NL_BLOCK, smem, st>>>(P, g, io, nl, status, tap_out);
+        } else if (tap == TAP_ACCEL) {
+            FP_CUDA(cudaFuncSetAttribute(nl_fast_kernel<TAP_ACCEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            nl_fast_kernel<TAP_ACCEL><<<ctas, NL_BLOCK, smem, st>>>(P, g, io, nl, status, tap_out);
+        } else {
+            set_error("internal: the list walk serves steps and the acceleration tap only");
+            return FP_ERR_INVALID;
+        }
+    } else {
+        if (tap != TAP_STEP) {
+            set_error("internal: the exact list walk serves steps only");
+            return FP_ERR_INVALID;
+        }
+        const int smem = (int)sizeof(NlWalkSmem);
+        FP_CUDA(cudaFuncSetAttribute(nl_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        nl_walk_kernel<<<ctas, NL_BLOCK, smem, st>>>(P, g, io, nl, status);
+    }
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;

@@ -200,7 +200,8 @@ class Simulation:
     def __init__(self, initial_positions, num_boids: int, bounding_box: Optional[BoundingBox] = None,
                  lead_boids: Optional[list] = None, obstacles: Optional[list] = None,
                  attractors: Optional[list] = None, *, seed: int = synth.SEED, device: int = 0,
-                 method: int = _lib.METHOD_AUTO, _state: Optional[np.ndarray] = None):
+                 method: int = _lib.METHOD_AUTO, numerics: Optional[int] = None,
+                 _state: Optional[np.ndarray] = None):
         """``Simulation::new`` (flocking.rs:63-95).  The reference jitters spawn points
         with an unseeded RNG; here the jitter comes from ``synth.spawn_flock(seed)``."""
         if _state is None:
@@ -216,6 +217,8 @@ class Simulation:
         state = f32c(_state, (-1, 6))
         self._h = self._create(state, device)
         check(self._lib.fp_flock_set_method(self._h, method))
+        if numerics is not None:
+            check(self._lib.fp_flock_set_numerics(self._h, numerics))
         self._push_tables()
 
     def _create(self, state: np.ndarray, device: int):
@@ -316,6 +319,17 @@ class Simulation:
         check(self._lib.fp_flock_get_method(self._h, C.byref(m)))
         return m.value
 
+    def set_numerics(self, numerics: int) -> None:
+        """``_lib.NUMERICS_EXACT`` (bit-identical arithmetic) or ``_lib.NUMERICS_FAST`` (neighbour
+        sets bit-exact, forces fused: accelerations within ~1e-6 relative)."""
+        check(self._lib.fp_flock_set_numerics(self._h, numerics))
+
+    def numerics(self):
+        """-> (requested, in use)"""
+        a, b = C.c_int(0), C.c_int(0)
+        check(self._lib.fp_flock_get_numerics(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def sync(self) -> None:
         check(self._lib.fp_flock_sync(self._h))
 
@@ -334,6 +348,12 @@ class Simulation:
         check(self._lib.fp_flock_read_local(self._h, ptr(idx), ptr(st)))
         return idx, st
 
+    def write_local(self, index, state) -> None:
+        """New values for the rows ``read_local`` listed, in that order (works on sharded flocks)."""
+        idx = np.ascontiguousarray(index, np.uint64)
+        st = f32c(state, (len(idx), 6))
+        check(self._lib.fp_flock_write_local(self._h, len(idx), ptr(idx), ptr(st)))
+
     def write_state(self, state) -> None:
         st = f32c(state, (self._n, 6))
         check(self._lib.fp_flock_write_state(self._h, ptr(st)))
@@ -343,6 +363,11 @@ class Simulation:
         fn = self._lib.fp_flock_read_instances_raw if raw else self._lib.fp_flock_read_instances
         check(fn(self._h, ptr(out)))
         return out
+
+    def export_instances(self, dst_ptr: int, raw: bool = False) -> None:
+        """``get_boid_instances`` written by the GPU into memory the caller maps (device memory or
+        pinned host memory): ``dst_ptr`` is the address, ``n x 8`` (or ``n x 25``) floats."""
+        check(self._lib.fp_flock_export_instances(self._h, C.c_void_p(dst_ptr), 1 if raw else 0))
 
     def read_accel(self, components: bool = False):
         acc = np.empty((self._n, 3), np.float32)

@@ -54,6 +54,23 @@ enum {
     FP_METHOD_SMALL = 3     /* one-CTA kernel for demo-sized flocks, multi-step in one launch */
 };
 
+/* Arithmetic of the boid-boid forces (ADDITION; the reference has one arithmetic, separately
+ * rounded f32).  Under either setting the neighbour sets -- the distance gate and the sight-angle
+ * test of boid.rs:149-157 -- are the reference's, bit for bit.
+ *   EXACT: every operation separately rounded in the reference's order; all-pairs and small
+ *          flocks are bit-identical to the Rust loop, the grid path to that loop run over the
+ *          boids in cell-sorted order (its summation order is the slot order of the binning, so
+ *          against the caller's order accelerations agree to ~1e-6 relative, and results depend
+ *          on the binning -- skin, re-binning plan, GPU count -- in the last bits).
+ *   FAST:  forces, attractor and bounding-box terms use fused multiply-add and MUFU.RSQ / RCP;
+ *          the sight-angle decision is taken on a fused cosine outside a 1e-5 guard band and by the
+ *          exact sequence inside it.  Accelerations agree with the reference to ~1e-6 relative
+ *          (north-star bar: 1e-5); all-pairs splits j across lanes with warp-shuffle reductions. */
+enum {
+    FP_NUMERICS_EXACT = 0,
+    FP_NUMERICS_FAST = 1
+};
+
 /* Status bits (fp_flock_status): raised where the reference would panic. */
 #define FP_STATUS_STEER_NEGATIVE 1u /* Duration::from_secs_f32(negative), obstacle.rs:25 */
 #define FP_STATUS_STEER_NAN_OVF 2u  /* Duration::from_secs_f32(NaN / overflow) */
@@ -80,6 +97,10 @@ int fp_flock_set_config(fp_flock *f, const fp_config *cfg);
 int fp_flock_get_config(fp_flock *f, fp_config *cfg);
 int fp_flock_set_method(fp_flock *f, int method);
 int fp_flock_get_method(fp_flock *f, int *method_in_use);
+/* FP_NUMERICS_*; in_use differs from the request when the configuration has thresholds FAST
+ * cannot filter (non-finite or inverted distance thresholds): the exact kernels run then. */
+int fp_flock_set_numerics(fp_flock *f, int numerics);
+int fp_flock_get_numerics(fp_flock *f, int *numerics, int *in_use);
 
 /* Simulation's Option<...> tables (flocking.rs:56-59); count 0 / NULL = None.
  * leads: n x [px py pz vx vy vz weight] (LeadBoid, boid.rs:13-18);
@@ -114,6 +135,13 @@ int fp_flock_read_instances(fp_flock *f, float *out8);
 /* Instance::to_raw (instance.rs:14-22, :39-44): n x 25 floats, column-major
  * 4x4 model then 3x3 normal matrix -- the 100-byte InstanceRaw record. */
 int fp_flock_read_instances_raw(fp_flock *f, float *out25);
+/* The same records written by the GPU straight into memory the caller maps: a device allocation
+ * (a mapped graphics-interop vertex buffer, cudaMalloc), or pinned host memory that the device can
+ * address (cudaHostAlloc / cudaHostRegister: the kernel's stores cross PCIe, no staging copy).
+ * Replaces the reference's per-instance queue.write_buffer loop (graphics/instance.rs:131-141).
+ * raw = 0: n x 8 floats (Instance), raw != 0: n x 25 floats (InstanceRaw).  Returns when the
+ * records are in place.  A pointer the device cannot address is FP_ERR_INVALID. */
+int fp_flock_export_instances(fp_flock *f, void *dst_device_visible, int raw);
 
 /* Debug taps for the parity tests (ADDITIONS).  All describe the CURRENT
  * state without advancing it.
@@ -197,6 +225,11 @@ int fp_flock_shard_info(fp_flock *f, int *rank, int *world, int *peer_mapped);
 int fp_flock_local_len(fp_flock *f, uint64_t *n_local);
 /* Local state with global indices: out_index n_local x u64, out_aos6 n_local x 6. */
 int fp_flock_read_local(fp_flock *f, uint64_t *out_index, float *out_aos6);
+/* New values for the boids this rank holds, in the order fp_flock_read_local lists them
+ * (index[k] must be the k-th index it returned): the sharded counterpart of
+ * fp_flock_write_state.  Every rank calls it (SPMD); the next step re-bins, and a boid whose new
+ * position lies in a neighbouring slab migrates there. */
+int fp_flock_write_local(fp_flock *f, uint64_t n_local, const uint64_t *index, const float *state_aos6);
 
 /* Self-test (ADDITION): compares the branch-free sqrt / division sequences of the grid walk
  * with __fsqrt_rn / __fdiv_rn bit for bit on n pseudo-random operand sets drawn from the

@@ -42,8 +42,9 @@ def py_config(orc_cfg) -> Config:
     return c
 
 
-def make_pair(orc_cfg, state, method, tables=None, device=0):
-    """-> (Simulation on the GPU, oracle Scene) describing the same flock."""
+def make_pair(orc_cfg, state, method, tables=None, device=0, numerics=_lib.NUMERICS_EXACT):
+    """-> (Simulation on the GPU, oracle Scene) describing the same flock.  EXACT numerics unless
+    asked otherwise: most parity tests compare bit patterns."""
     t = tables or {}
     sim = Simulation.from_state(
         state,
@@ -53,7 +54,7 @@ def make_pair(orc_cfg, state, method, tables=None, device=0):
         obstacles=[Obstacle(o[:3], float(o[3])) for o in t["obstacles"]] if "obstacles" in t else None,
         attractors=([PointAttractor(a[:3], float(a[3])) for a in t["attractors"]]
                     if "attractors" in t else None),
-        method=method, device=device)
+        method=method, device=device, numerics=numerics)
     sim.set_config(py_config(orc_cfg))
     scene = Scene(leads=t.get("leads"), attractors=t.get("attractors"),
                   obstacles=t.get("obstacles"), bbox=t.get("bbox"))

@@ -228,3 +228,25 @@ def test_instances_match_oracle(orc):
     assert np.allclose(np.linalg.norm(raw[:, 0:3], axis=1), 0.1, atol=1e-6)
     inst = sim.get_boid_instances()
     assert len(inst) == 1000 and inst[5].scale == float(f32(0.1))
+
+
+def test_instances_exported_into_mapped_and_device_buffers(orc):
+    """fp_flock_export_instances: the GPU writes the Instance / InstanceRaw records straight into a
+    buffer the caller maps -- pinned host memory (stores cross PCIe, no staging copy) and device
+    memory (what a mapped graphics-interop vertex buffer is) -- same bits as the staged read-out;
+    pageable memory is refused."""
+    import torch
+    st = synth.uniform_flock(5000, 60.0, seed=52)
+    sim, _ = make_pair(orc.default_config(), st, _lib.METHOD_GRID)
+    sim.step_many(3)
+    for raw, width in ((False, 8), (True, 25)):
+        ref = sim.read_instances(raw=raw)
+        pinned = torch.zeros((len(st), width), dtype=torch.float32).pin_memory()
+        sim.export_instances(pinned.data_ptr(), raw=raw)
+        assert np.array_equal(bits(pinned.numpy()), bits(ref))
+        dev = torch.zeros((len(st), width), dtype=torch.float32, device="cuda")
+        sim.export_instances(dev.data_ptr(), raw=raw)
+        assert np.array_equal(bits(dev.cpu().numpy()), bits(ref))
+    pageable = np.zeros((len(st), 8), np.float32)
+    with pytest.raises(_lib.FeriphysError):
+        sim.export_instances(pageable.ctypes.data)

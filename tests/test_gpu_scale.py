@@ -1,0 +1,112 @@
+"""-m gpu parity at the sizes BASELINE.json quotes: C2 (100k all-pairs), C4 (2^24 grid),
+C5 (2^22 grid with leads, attractors, obstacles and a bounding box).
+
+At these sizes the oracle evaluates a sample of rows (the grid-accelerated oracle is bit-identical
+to the literal loops, tests/test_oracle_grid.py): neighbour sets of the sampled rows bit-exact,
+accelerations within 1e-5 relative, at step 0 and again after the flock has been stepped across
+several re-binnings -- under both numerics."""
+import os
+
+import numpy as np
+import pytest
+
+from feriphys_b200 import _lib, synth
+from feriphys_b200.flocking import LeadBoid
+from gpu_util import FixedLead, make_pair, rel_err
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+NT = os.cpu_count() or 1
+ACC_RTOL = 1e-5
+NUM = {"exact": _lib.NUMERICS_EXACT, "fast": _lib.NUMERICS_FAST}
+
+
+def _sampled(orc, sim, c, sc, state, windows, literal=False):
+    gc, gh = sim.read_neighbors()
+    ga = sim.read_accel()
+    worst = 0.0
+    for lo, hi in windows:
+        rc, rh, _ = orc.neighbors_rows(c, state, lo, hi, threads=NT, grid=not literal)
+        assert np.array_equal(gc[lo:hi], rc), "neighbour counts differ"
+        assert np.array_equal(gh[lo:hi], rh), "neighbour sets differ"
+        ra, _, _ = orc.accel_rows(c, sc, state, lo, hi, threads=NT, grid=not literal)
+        worst = max(worst, rel_err(ga[lo:hi], ra))
+    assert worst <= ACC_RTOL, worst
+    return gc
+
+
+@pytest.mark.parametrize("numerics", ["exact", "fast"])
+def test_c4_sixteen_million_boids_sampled_rows(orc, numerics):
+    n = 1 << 24
+    st = synth.uniform_flock(n, 2048.0)
+    c = orc.default_config()
+    sim, sc = make_pair(c, st, _lib.METHOD_GRID, numerics=NUM[numerics])
+    win = ((0, 4096), (n - 4096, n))
+    gc = _sampled(orc, sim, c, sc, st, win)
+    assert 12 < gc.mean() < 22
+    sim.set_rebin(skin=0.12)          # ~20 steps per binning: the 50 steps below cross two of them
+    sim.step_many(50)
+    skin, nsteps, rebins, replayed = sim.rebin_info()
+    assert nsteps == 50 and rebins >= 3
+    s1 = sim.read_state()
+    assert np.isfinite(s1).all()
+    _sampled(orc, sim, c, sc, s1, win)
+    assert sim.status() == 0
+
+
+@pytest.mark.parametrize("numerics", ["exact", "fast"])
+def test_c5_four_million_boids_with_tables_sampled_rows(orc, numerics):
+    n, extent = 1 << 22, 1296.0
+    st = synth.uniform_flock(n, extent)
+    att, obs, bbox = synth.c5_tables(extent)
+    # eight lead boids at rest at spread positions (weight 10, boid.rs:35-44)
+    u = synth.u01(synth.SEED ^ 0x1EAD, 8, 3)
+    leads = np.zeros((8, 7), f32)
+    leads[:, :3] = u * f32(extent)
+    leads[:, 3:6] = 0.5
+    leads[:, 6] = 10.0
+    tables = dict(attractors=att, obstacles=obs, bbox=bbox, leads=leads)
+    c = orc.default_config()
+    sim, sc = make_pair(c, st, _lib.METHOD_GRID, tables, numerics=NUM[numerics])
+    win = ((0, 4096), (n - 4096, n))
+    _sampled(orc, sim, c, sc, st, win)
+    # rows near the tables: the boids closest to a lead, an obstacle and an attractor
+    for centre in (leads[0, :3], obs[0, :3], att[0, :3], att[5, :3]):
+        i = int(np.argmin(np.linalg.norm(st[:, :3] - centre, axis=1)))
+        lo = max(0, min(i - 64, n - 128))
+        _sampled(orc, sim, c, sc, st, ((lo, lo + 128),))
+    sim.set_rebin(skin=0.12)
+    sim.step_many(40)
+    skin, nsteps, rebins, replayed = sim.rebin_info()
+    assert nsteps == 40 and rebins >= 2
+    s1 = sim.read_state()
+    _sampled(orc, sim, c, sc, s1, win)
+
+
+@pytest.mark.parametrize("numerics", ["exact", "fast"])
+def test_c2_hundred_thousand_boids_allpairs_literal_rows(orc, numerics):
+    n = 100_000
+    st = synth.uniform_flock(n, 24.0)
+    c = orc.default_config(max_sight_angle=float(f32(3.14159274101257324)),
+                           centering_factor=float(f32(0.1) * f32(110.0) / f32(n)),
+                           velocity_matching_factor=float(f32(0.5) * f32(110.0) / f32(n)))
+    sim, sc = make_pair(c, st, _lib.METHOD_ALLPAIRS, numerics=NUM[numerics])
+    # 4096 rows against the LITERAL O(N) loop of flocking.rs:133-151 (no grid in the oracle)
+    win = ((0, 2048), (n - 2048, n))
+    gc, gh = sim.read_neighbors()
+    ga = sim.read_accel()
+    for lo, hi in win:
+        rc, rh, _ = orc.neighbors_rows(c, st, lo, hi, threads=NT)
+        assert np.array_equal(gc[lo:hi], rc) and np.array_equal(gh[lo:hi], rh)
+        ra, _, _ = orc.accel_rows(c, sc, st, lo, hi, threads=NT)
+        if numerics == "exact":
+            assert np.array_equal(ga[lo:hi].view(np.uint32), ra.view(np.uint32))   # same order, same bits
+        else:
+            assert rel_err(ga[lo:hi], ra) <= ACC_RTOL
+    assert 20000 < gc.mean() < 60000          # dense: tens of thousands of in-range neighbours each
+    sim.step_many(3)
+    cur = st
+    for _ in range(3):
+        cur, _ = orc.step(c, sc, cur, threads=NT, grid=True)
+    out = sim.read_state()
+    assert np.abs(out - cur).max() <= 1e-5 * max(1.0, float(np.abs(cur).max()))

@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """GPU: step a grid flock and print one JSON line with a hash of the final state.
 
-Used to compare walk kernels selected by FP_WALK_VARIANT (31 = production, 41 = standing
-candidate lists, fp_walk_nl.cu), which must agree bit for bit as long as both keep the same
-binnings: run it once per variant with the same arguments and compare `sha256`.
+Used to compare the walk on standing candidate lists (fp_walk_nl.cu, the default) with the plain
+staged walk (FP_NL=0), which must agree bit for bit under EXACT numerics as long as both keep the
+same binnings (pin the skin with FP_SKIN): run it once per setting and compare `sha256`.
 
     python tools/nl_state_hash.py [n] [extent] [steps] [seed] [blob]
 
 `blob` > 0 adds that many boids inside a ball of radius 6 (thousands of neighbours each: the
-candidate lists overflow and the library must fall back to the production walk)."""
+candidate lists overflow and the library must fall back to the staged walk)."""
 import hashlib
 import json
 import os
@@ -63,7 +63,7 @@ def main():
     ms = 1e3 * (time.perf_counter() - t0) / steps
     out = sim.read_state()
     skin, nsteps, rebins, replayed = sim.rebin_info()
-    print(json.dumps({"variant": os.environ.get("FP_WALK_VARIANT", "default"), "boids": len(st), "steps": steps,
+    print(json.dumps({"lists": os.environ.get("FP_NL", "1") != "0", "boids": len(st), "steps": steps,
                       "sha256": hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest(),
                       "skin": skin, "rebins": int(rebins), "replayed": int(replayed), "wall_ms_per_step": ms,
                       "finite": bool(np.isfinite(out).all())}))

@@ -2,7 +2,8 @@
 """GPU: one flock taken through the state transitions that surround the walk -- taps that re-bin,
 an outrun plan with replays, a config switch (steering overrides on and off), tables, a new state
 from the host, a detour through the all-pairs kernel -- printing a hash of the state after each
-stage.  Run once per FP_WALK_VARIANT and compare the lines: every variant must print the same."""
+stage.  Run once with the candidate lists (default) and once without (FP_NL=0), the skin pinned by
+FP_SKIN: both must print the same lines."""
 import hashlib
 import os
 import sys
@@ -20,7 +21,7 @@ f32 = np.float32
 
 
 def main():
-    v = os.environ.get("FP_WALK_VARIANT", "default")
+    v = "lists" if os.environ.get("FP_NL", "1") != "0" else "staged walk"
     stage = [0]
 
     def show(sim, what):
@@ -29,7 +30,7 @@ def main():
         print(f"{stage[0]:2d} {what:34s} {hashlib.sha256(st.tobytes()).hexdigest()[:16]} "
               f"rebin_info {sim.rebin_info()[1:]} finite {bool(np.isfinite(st).all())}", flush=True)
 
-    print("variant", v)
+    print("walk:", v)
     st = synth.uniform_flock(40000, 270.0, seed=21)
     sim = Simulation.from_state(st, method=_lib.METHOD_GRID,
                                 attractors=[PointAttractor(np.array([-60, 80, 80], f32), 2.0e4)],

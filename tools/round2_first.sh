@@ -21,7 +21,7 @@ FP_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -x -q > $
 tail -3 $O/r2_nl_tests.log
 # 2. bench lines, production vs lists
 for w in c4 c3 c5; do
-  for v in 31 41 43 44 45 46 47; do
+  for v in 31 41 43 44 45 46 47; do  # (each line ~10-25 s)
     FP_WALK_VARIANT=$v python bench.py --workload $w --no-cpu-baseline > $O/r2_bench_${w}_v$v.json 2>> $O/r2.err
   done
 done
