@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libferiphys_cuda.so")
 OK = 0
 METHOD_AUTO, METHOD_ALLPAIRS, METHOD_GRID, METHOD_SMALL = 0, 1, 2, 3
 NUMERICS_EXACT, NUMERICS_FAST = 0, 1
+STATEFUL_TEST_POINT, STATEFUL_TEST_EXAMPLEFN, STATEFUL_SPRINGY_POINT, STATEFUL_RIGIDBODY, STATEFUL_BOID = 1, 2, 3, 4, 5
 STATUS_STEER_NEGATIVE, STATUS_STEER_NAN_OVF = 1, 2
 
 
@@ -84,6 +85,20 @@ _PROTOS = {
     "fp_flock_state_rk4": (C.c_int, [_P, C.c_float]),
     "fp_state_euler_combine": (C.c_int, [C.c_int, C.c_size_t, _P, _P, C.c_float, _P]),
     "fp_state_rk4_combine": (C.c_int, [C.c_int, C.c_size_t, _P, _P, _P, _P, _P, C.c_float, _P]),
+    "fp_state_num_state_elements": (C.c_int, [C.c_int]),
+    "fp_state_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_uint64, _P]),
+    "fp_state_destroy": (C.c_int, [_P]),
+    "fp_state_len": (C.c_uint64, [_P]),
+    "fp_state_write": (C.c_int, [_P, _P]),
+    "fp_state_read": (C.c_int, [_P, _P]),
+    "fp_state_derivative": (C.c_int, [_P, _P]),
+    "fp_state_euler_step": (C.c_int, [_P, C.c_float, C.c_uint32]),
+    "fp_state_rk4_step": (C.c_int, [_P, C.c_float, C.c_uint32]),
+    "fp_state_sync": (C.c_int, [_P]),
+    "fp_state_device_vector": (C.c_int, [_P, C.POINTER(_P)]),
+    "fp_state_time_steps": (C.c_int, [_P, C.c_float, C.c_int, C.c_uint32, C.POINTER(C.c_float)]),
+    "fp_sph_neighbors": (C.c_int, [C.c_int, C.c_uint64, _P, C.c_uint32, C.c_float, C.c_float, _P, _P, _P,
+                                   C.POINTER(C.c_float)]),
     "fp_nccl_unique_id": (C.c_int, [_P]),
     "fp_flock_create_sharded": (C.c_int, [C.POINTER(_P), C.POINTER(FpConfig), C.c_uint64, C.c_uint64,
                                           C.c_uint64, _P, C.c_int, C.c_int, C.c_int, _P]),

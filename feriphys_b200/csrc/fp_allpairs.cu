@@ -311,35 +311,42 @@ struct ApfBoid {
     float ax, ay, az;      // partial acceleration
 };
 
+// FOV = false: the configuration never culls (max_sight_angle >= pi, the C2 workload): the cosine is
+// not evaluated at all.  Branch-free but for the rare exact path: in a dense flock nearly every batch
+// reaches this code, and a branch per pair would only add its own overhead to the same issue slots.
+template <bool FOV>
 __device__ __forceinline__ void apf_pair(const DevParams &P, ApfBoid &b, const float4 pj, const float4 *tvj,
                                          bool live) {
     // (the fast grid walk's pair, fp_walk_nl.cu: fast_gate + fast_force)
     const Self &self = b.self;
     const float dx = fsub(pj.x, self.p.x), dy = fsub(pj.y, self.p.y), dz = fsub(pj.z, self.p.z);
     const float m2 = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
-    const float q = fmaf(self.vhat.z, dz, fmaf(self.vhat.y, dy, self.vhat.x * dx));
     const float r = rsqrt_seed(m2);
-    const float c = q * r;
-    const float gc = (c - P.fz_a) * (c - P.fz_b);
     const bool in = live && !(m2 >= P.m2_cut);
-    const bool clear = fabsf(gc) > P.fz_gc_tol && m2 >= 1e-12f;
-    if (in && clear && gc > 0.0f) {
-        const float4 vj = *tvj;
-        const float g0 = m2 * r, h = 0.5f * r;
-        const float mag = fmaf(fmaf(-g0, g0, m2), h, g0);
-        const float coef = fmaf(P.f_c, mag, P.neg_f_a * (r * r)) * r;
-        const float w = m2 <= P.m2_one ? 1.0f : (mag - P.thr) * P.fz_rinv_fall;
-        const float dvx = vj.x - self.v.x, dvy = vj.y - self.v.y, dvz = vj.z - self.v.z;
-        const bool vsm = fmaxf(fmaxf(fabsf(dvx), fabsf(dvy)), fabsf(dvz)) <= FP_F32_EPSILON;
-        const float cw = coef * w, fw = vsm ? 0.0f : P.f_v * w;
-        b.ax = fmaf(cw, dx, fmaf(fw, dvx, b.ax));
-        b.ay = fmaf(cw, dy, fmaf(fw, dvy, b.ay));
-        b.az = fmaf(cw, dz, fmaf(fw, dvz, b.az));
-    } else if (in && !clear) {
+    bool clear = m2 >= 1e-12f, vis = true;
+    if (FOV) {
+        const float q = fmaf(self.vhat.z, dz, fmaf(self.vhat.y, dy, self.vhat.x * dx));
+        const float c = q * r;
+        const float gc = (c - P.fz_a) * (c - P.fz_b);
+        clear = clear && fabsf(gc) > P.fz_gc_tol;
+        vis = gc > 0.0f;
+    }
+    const bool pass = in && clear && vis;
+    const float4 vj = *tvj;
+    const float g0 = m2 * r, h = 0.5f * r;
+    const float mag = fmaf(fmaf(-g0, g0, m2), h, g0);
+    const float coef = fmaf(P.f_c, mag, P.neg_f_a * (r * r)) * r;
+    const float w = m2 <= P.m2_one ? 1.0f : (mag - P.thr) * P.fz_rinv_fall;
+    const float dvx = vj.x - self.v.x, dvy = vj.y - self.v.y, dvz = vj.z - self.v.z;
+    const bool vsm = fmaxf(fmaxf(fabsf(dvx), fabsf(dvy)), fabsf(dvz)) <= FP_F32_EPSILON;
+    const float cw = pass ? coef * w : 0.0f, fw = (pass && !vsm) ? P.f_v * w : 0.0f;  // (selected: see fp_walk_nl.cu)
+    b.ax = fmaf(cw, dx, fmaf(fw, dvx, b.ax));
+    b.ay = fmaf(cw, dy, fmaf(fw, dvy, b.ay));
+    b.az = fmaf(cw, dz, fmaf(fw, dvz, b.az));
+    if (in && !clear) {
         // guard band / coincident / NaN (rare; the boid's own record lands here once): exact sequence.
         // The reference skips records equal to the boid (flocking.rs:137-139); their exact
         // contribution is +0 for finite states, so evaluating them changes nothing.
-        const float4 vj = *tvj;
         V3 contrib;
         if (pair_inrange<false>(P, self, v3(dx, dy, dz), m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar, contrib)) {
             b.ax += contrib.x;
@@ -349,7 +356,7 @@ __device__ __forceinline__ void apf_pair(const DevParams &P, ApfBoid &b, const f
     }
 }
 
-template <int TAP>
+template <int TAP, bool FOV>
 __global__ void __launch_bounds__(AP_BLOCK, 4)
 allpairs_fast_kernel(const DevParams P, const float4 *__restrict__ pos_all, const float4 *__restrict__ vel_all,
                      uint32_t n_all, uint32_t row0, uint32_t nrows, int js_log2, const float *__restrict__ bounds8,
@@ -436,8 +443,8 @@ allpairs_fast_kernel(const DevParams P, const float4 *__restrict__ pos_all, cons
                     for (int u = 0; u < 4; ++u) {
                         const uint32_t t = 4 * q + u;
                         const float4 pj = S.tp[t];
-                        apf_pair(P, b[0], pj, &S.tv[t], t < cnt);
-                        apf_pair(P, b[1], pj, &S.tv[t], t < cnt);
+                        apf_pair<FOV>(P, b[0], pj, &S.tv[t], t < cnt);
+                        apf_pair<FOV>(P, b[1], pj, &S.tv[t], t < cnt);
                     }
                 }
             }
@@ -510,12 +517,16 @@ int launch_allpairs(cudaStream_t st, const DevParams &P, int tap, const float4 *
         const int js = apf_js_log2(nrows);
         const uint32_t rows_per_cta = 2u * (AP_BLOCK >> js);
         const dim3 gridf((nrows + rows_per_cta - 1) / rows_per_cta);
-        if (tap == TAP_STEP)
-            allpairs_fast_kernel<TAP_STEP><<<gridf, AP_BLOCK, 0, st>>>(P, pos_all, vel_all, n_all, row0, nrows, js, bounds8,
-                                                                     pos_out, vel_out, status, tap_out);
-        else
-            allpairs_fast_kernel<TAP_ACCEL><<<gridf, AP_BLOCK, 0, st>>>(P, pos_all, vel_all, n_all, row0, nrows, js, bounds8,
-                                                                      pos_out, vel_out, status, tap_out);
+        const bool fov = P.fz_a > -2.5f;  // (-3: the configuration never culls)
+#define FP_APF(T, F)                                                                                        \
+    allpairs_fast_kernel<T, F><<<gridf, AP_BLOCK, 0, st>>>(P, pos_all, vel_all, n_all, row0, nrows, js, bounds8, \
+                                                           pos_out, vel_out, status, tap_out)
+        if (tap == TAP_STEP) {
+            if (fov) FP_APF(TAP_STEP, true); else FP_APF(TAP_STEP, false);
+        } else {
+            if (fov) FP_APF(TAP_ACCEL, true); else FP_APF(TAP_ACCEL, false);
+        }
+#undef FP_APF
         count_launch();
         FP_CUDA(cudaGetLastError());
         return FP_OK;

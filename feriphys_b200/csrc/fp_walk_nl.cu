@@ -364,59 +364,87 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
 }
 
 // ---- FAST numerics ----------------------------------------------------------------------------
+constexpr int NF_CAP = 32;  // survivor list (shared memory); a fuller list is drained mid-way
+
 struct NlFastSmem {
     alignas(16) float tx[NF_TILE + 8], ty[NF_TILE + 8], tz[NF_TILE + 8];
     alignas(16) float4 tv[NF_TILE];  // velocities of the staged candidates (.w: record flag, unused)
+    uint16_t list[NF_CAP][NL_BLOCK];  // per-thread survivors: tile offset | 0x8000 if the exact sequence must decide
     uint32_t toff[10], tslot[9];
-    alignas(8) uint64_t bar;
+    alignas(8) uint64_t bar, bar_v;   // positions / velocities have landed
 };
 
 // One entry of a boid's cached list under FAST numerics.  The squared distance is the reference's
 // own (separately rounded, boid.rs:94-96 through cgmath's dot), so "in range" and "weight 1" are its
 // decisions.  The cosine of the sight angle is fused and uses MUFU.RSQ: within ~1e-6 of the
 // reference's (boid.rs:102-105); the decision is taken on it when it is further than the guard band
-// from both ends of the culled interval [-1, cstar], else `unsure` sends the pair down the exact path.
-struct FastPair {
-    float dx, dy, dz, m2, r;
-    bool pass;    // contributes, decided outside the guard bands
-    bool unsure;  // in range but degenerate or inside a guard band: the exact sequence decides
-};
-__device__ __forceinline__ FastPair fast_gate(const DevParams &P, const Self &self, float px, float py, float pz,
-                                              bool live) {
-    FastPair f;
-    f.dx = fsub(px, self.p.x);
-    f.dy = fsub(py, self.p.y);
-    f.dz = fsub(pz, self.p.z);
-    f.m2 = fadd(fadd(fmul(f.dx, f.dx), fmul(f.dy, f.dy)), fmul(f.dz, f.dz));
-    const float q = fmaf(self.vhat.z, f.dz, fmaf(self.vhat.y, f.dy, self.vhat.x * f.dx));
-    f.r = rsqrt_seed(f.m2);
-    const float c = q * f.r;
+// from both ends of the culled interval [-1, cstar], else the pair goes down the exact path.
+// -> 0: no contribution, 1: contributes, 2: the exact sequence must decide
+__device__ __forceinline__ int fast_gate(const DevParams &P, const Self &self, float px, float py, float pz) {
+    const float dx = fsub(px, self.p.x), dy = fsub(py, self.p.y), dz = fsub(pz, self.p.z);
+    const float m2 = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+    const float q = fmaf(self.vhat.z, dz, fmaf(self.vhat.y, dy, self.vhat.x * dx));
+    const float c = q * rsqrt_seed(m2);
     const float gc = (c - P.fz_a) * (c - P.fz_b);   // <= 0: culled (acosf(c) > max_sight_angle)
-    const bool in = live && !(f.m2 >= P.m2_cut);
+    if (m2 >= P.m2_cut) return 0;
     // coincident positions (abs_diff_eq! guards, boid.rs:111,121), NaN, and cosines in the guard band
-    const bool clear = fabsf(gc) > P.fz_gc_tol && f.m2 >= 1e-12f;
-    f.unsure = in && !clear;
-    f.pass = in && clear && gc > 0.0f;
-    return f;
+    if (!(fabsf(gc) > P.fz_gc_tol) || !(m2 >= 1e-12f)) return 2;
+    return gc > 0.0f ? 1 : 0;
 }
-// contribution of a pair that passed, accumulated with FMAs: w_d ((av + ce) + vm)  (boid.rs:162-165)
-__device__ __forceinline__ void fast_force(const DevParams &P, const Self &self, const FastPair &f, float4 vj,
-                                           float &ax, float &ay, float &az) {
+// contribution of a survivor, accumulated with FMAs: w_d ((av + ce) + vm)  (boid.rs:162-165)
+__device__ __forceinline__ void fast_force(const DevParams &P, const Self &self, float px, float py, float pz,
+                                           float4 vj, bool live, float &ax, float &ay, float &az) {
+    const float dx = fsub(px, self.p.x), dy = fsub(py, self.p.y), dz = fsub(pz, self.p.z);
+    const float m2 = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+    const float r = rsqrt_seed(m2);
     // dist: the seed refined to the correctly rounded square root (it enters the ramp by difference)
-    const float g0 = f.m2 * f.r, h = 0.5f * f.r;
-    const float mag = fmaf(fmaf(-g0, g0, f.m2), h, g0);
-    const float coef = fmaf(P.f_c, mag, P.neg_f_a * (f.r * f.r)) * f.r;  // ((-f_a / d^2) + f_c d) / d, on d
-    const float w = f.m2 <= P.m2_one ? 1.0f : (mag - P.thr) * P.fz_rinv_fall;  // boid.rs:152-161 (F7)
+    const float g0 = m2 * r, h = 0.5f * r;
+    const float mag = fmaf(fmaf(-g0, g0, m2), h, g0);
+    const float coef = fmaf(P.f_c, mag, P.neg_f_a * (r * r)) * r;  // ((-f_a / d^2) + f_c d) / d, on d
+    const float w = m2 <= P.m2_one ? 1.0f : (mag - P.thr) * P.fz_rinv_fall;  // boid.rs:152-161 (F7)
     const float dvx = vj.x - self.v.x, dvy = vj.y - self.v.y, dvz = vj.z - self.v.z;
     const bool vsm = fmaxf(fmaxf(fabsf(dvx), fabsf(dvy)), fabsf(dvz)) <= FP_F32_EPSILON;  // boid.rs:132
-    const float cw = coef * w, fw = vsm ? 0.0f : P.f_v * w;
-    ax = fmaf(cw, f.dx, fmaf(fw, dvx, ax));
-    ay = fmaf(cw, f.dy, fmaf(fw, dvy, ay));
-    az = fmaf(cw, f.dz, fmaf(fw, dvz, az));
+    // (selected, not multiplied by zero: an idle lane may have evaluated its own record, m2 = 0)
+    const float cw = live ? coef * w : 0.0f, fw = (live && !vsm) ? P.f_v * w : 0.0f;
+    ax = fmaf(cw, dx, fmaf(fw, dvx, ax));
+    ay = fmaf(cw, dy, fmaf(fw, dvy, ay));
+    az = fmaf(cw, dz, fmaf(fw, dvz, az));
+}
+
+// the force phase over a thread's survivor list (two entries per trip: independent chains)
+__device__ __forceinline__ void fast_drain(const DevParams &P, const Self &self, const NlFastSmem &S,
+                                           const uint16_t *lst, int nb, int nb_warp, float &ax, float &ay, float &az) {
+#pragma unroll 1
+    for (int k = 0; k < nb_warp; k += 2) {
+        const bool la = k < nb, lb = k + 1 < nb;
+        const uint32_t ea = la ? lst[k * NL_BLOCK] : 0u, eb = lb ? lst[(k + 1) * NL_BLOCK] : 0u;
+        const uint32_t ta = ea & 0xfffu, tb = eb & 0xfffu;
+        const float4 va = S.tv[ta], vb = S.tv[tb];
+        // (an idle lane evaluates tile entry 0 with weight 0: finite data, nothing added)
+        fast_force(P, self, S.tx[ta], S.ty[ta], S.tz[ta], va, la && !(ea & 0x8000u), ax, ay, az);
+        fast_force(P, self, S.tx[tb], S.ty[tb], S.tz[tb], vb, lb && !(eb & 0x8000u), ax, ay, az);
+        if ((ea | eb) & 0x8000u) {
+            // guard band / degenerate pair (rare): the reference's own sequence decides and evaluates
+#pragma unroll 1
+            for (int u = 0; u < 2; ++u) {
+                const uint32_t e = u ? eb : ea, t = e & 0xfffu;
+                if (!(e & 0x8000u)) continue;
+                V3 d, contrib;
+                const float m2 = pair_m2(self, v3(S.tx[t], S.ty[t], S.tz[t]), d);
+                const float4 vj = S.tv[t];
+                if (!(m2 >= P.m2_cut) &&
+                    pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar, contrib)) {
+                    ax += contrib.x;
+                    ay += contrib.y;
+                    az += contrib.z;
+                }
+            }
+        }
+    }
 }
 
 template <int TAP>
-__global__ void __launch_bounds__(NL_BLOCK, 5)
+__global__ void __launch_bounds__(NL_BLOCK, 4)
 nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO nl, unsigned *__restrict__ status,
                TapOut tap) {
     if (TAP == TAP_STEP && io.ctl && io.ctl->stale) return;  // lazy re-binning: this step is void
@@ -425,8 +453,44 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     const uint32_t tid = threadIdx.x;
     const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
     const bool active = s < io.last;
-    if (tid == 0) mbar_init(&S.bar, 1);
-
+    const uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
+    const bool no_lists = __ldg(tab + 18) != 0u;
+    if (tid < 32 && !no_lists) {
+        // warp 0 gets the tile moving before anything else: layout from the build's record, positions
+        // on one barrier, velocities (needed only by the force phase) on a second one
+        if (tid == 0) {
+            mbar_init(&S.bar, 1);
+            mbar_init(&S.bar_v, 1);
+        }
+        __syncwarp();
+        const uint32_t ub = tid < 9 ? __ldg(tab + tid) : 0u, ue = tid < 9 ? __ldg(tab + 9 + tid) : 0u;
+        const uint32_t len = ue - ub;
+        uint32_t inc = len;  // inclusive prefix sum over the lanes
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+            if ((int)tid >= off) inc += t;
+        }
+        const uint32_t toff = inc - len, total = __shfl_sync(0xffffffffu, inc, 8);
+        if (tid < 9) {
+            S.toff[tid] = toff;
+            S.tslot[tid] = ub - toff;
+        }
+        if (tid == 0) {
+            S.toff[9] = total;
+            if (total) {
+                mbar_expect_tx(&S.bar, total * 12u);
+                mbar_expect_tx(&S.bar_v, total * 16u);
+            }
+        }
+        __syncwarp();
+        if (tid < 9 && len) {  // (a layout with lists always fits the tile: the build saw to that)
+            bulk_g2s(&S.tx[toff], io.soa_in[0] + ub, len * 4u, &S.bar);
+            bulk_g2s(&S.ty[toff], io.soa_in[1] + ub, len * 4u, &S.bar);
+            bulk_g2s(&S.tz[toff], io.soa_in[2] + ub, len * 4u, &S.bar);
+            bulk_g2s(&S.tv[toff], io.vel_s + ub, len * 16u, &S.bar_v);
+        }
+    }
     float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
     uint32_t n_c = 0;
     if (active) {
@@ -447,25 +511,28 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
         work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
     }
     if (!work) n_c = 0;
-    const uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
-    if (__ldg(tab + 18)) {  // a CTA without lists
+    if (no_lists) {  // a CTA without lists
         V3 acc = v3zero();
         if (work) acc = nl_walk_global(P, g, io, s, self);
         if (active) walk_finish<TAP, true>(P, s, pi4, vi4, self, acc, 0u, 0ull, io, status, tap);
         return;
     }
-    __syncthreads();  // the barrier is initialised
-    if (tid < 32) {
-        const uint32_t ub = tid < 9 ? __ldg(tab + tid) : 0u, ue = tid < 9 ? __ldg(tab + 9 + tid) : 0u;
-        nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], NF_TILE, S.tv, io.vel_s);
-    }
-    __syncthreads();
     const uint32_t nmax = __reduce_max_sync(0xffffffffu, n_c);
-    if (S.toff[9] > 0) mbar_wait(&S.bar, 0);
+    __syncthreads();  // the barriers are initialised, the layout is in shared memory
+    const bool staged = S.toff[9] > 0;
+    if (staged) mbar_wait(&S.bar, 0);
 
+    uint16_t *const lst = &S.list[0][tid];  // entry k at lst[k * BLOCK]
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    int cnt = 0;
+    bool vel_ready = !staged;
 #pragma unroll 1
     for (uint32_t k = 0; k < nmax; k += 4) {
+        if (__any_sync(0xffffffffu, cnt > NF_CAP - 4)) {  // some lane's list may not take another batch
+            if (!vel_ready) { mbar_wait(&S.bar_v, 0); vel_ready = true; }
+            fast_drain(P, self, S, lst, cnt, (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt), ax, ay, az);
+            cnt = 0;
+        }
         const uint32_t c[4] = {e0, e1, e2, e3};
         if (k + 4 < nmax) {
             e0 = __ldcs(vlp + (size_t)(k + 4) * NL_BLOCK);
@@ -473,37 +540,23 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
             e2 = __ldcs(vlp + (size_t)(k + 6) * NL_BLOCK);
             e3 = __ldcs(vlp + (size_t)(k + 7) * NL_BLOCK);
         }
-        FastPair f[4];
-        uint32_t t[4];
         const uint32_t rem = n_c > k ? n_c - k : 0u;  // live entries of this batch
-        bool any_unsure = false;
+        int verdict[4];
+        uint32_t t[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             t[u] = c[u] & 0xfffu;  // (entries past n_c hold offsets of earlier builds: inside the arrays, unused)
-            f[u] = fast_gate(P, self, S.tx[t[u]], S.ty[t[u]], S.tz[t[u]], (uint32_t)u < rem);
-            any_unsure |= f[u].unsure;
+            verdict[u] = fast_gate(P, self, S.tx[t[u]], S.ty[t[u]], S.tz[t[u]]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (f[u].pass) fast_force(P, self, f[u], S.tv[t[u]], ax, ay, az);
-        if (any_unsure) {
-            // guard band / degenerate pair (rare): the reference's own sequence decides and evaluates
-#pragma unroll 1
-            for (uint32_t u = 0; u < 4; ++u) {
-                const uint32_t tu = (u == 0 ? c[0] : u == 1 ? c[1] : u == 2 ? c[2] : c[3]) & 0xfffu;
-                const FastPair fu = fast_gate(P, self, S.tx[tu], S.ty[tu], S.tz[tu], u < rem);
-                if (!fu.unsure) continue;
-                const float4 vj = S.tv[tu];
-                V3 contrib;
-                if (pair_inrange<false>(P, self, v3(fu.dx, fu.dy, fu.dz), fu.m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar,
-                                        contrib)) {
-                    ax += contrib.x;
-                    ay += contrib.y;
-                    az += contrib.z;
-                }
+            if ((uint32_t)u < rem && verdict[u]) {
+                lst[cnt * NL_BLOCK] = (uint16_t)(t[u] | (verdict[u] == 2 ? 0x8000u : 0u));
+                ++cnt;
             }
-        }
     }
+    if (!vel_ready) mbar_wait(&S.bar_v, 0);
+    fast_drain(P, self, S, lst, cnt, (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt), ax, ay, az);
     if (!active) return;
     walk_finish<TAP, true>(P, s, pi4, vi4, self, v3(ax, ay, az), 0u, 0ull, io, status, tap);
 }

@@ -25,9 +25,11 @@ def _splitmix64(x: np.ndarray) -> np.ndarray:
         return z ^ (z >> np.uint64(31))
 
 
-def u01(seed: int, n: int, components: int = 6, first: int = 0) -> np.ndarray:
-    """``[n, components]`` float32 in [0,1), keyed by (seed, index, component)."""
-    idx = np.arange(first, first + n, dtype=np.uint64)[:, None] * np.uint64(components)
+def u01(seed: int, n: int, components: int = 6, first: int = 0, index=None) -> np.ndarray:
+    """``[n, components]`` float32 in [0,1), keyed by (seed, index, component).  ``index``: explicit
+    boid indices instead of ``first .. first + n``."""
+    rows = np.arange(first, first + n, dtype=np.uint64) if index is None else np.asarray(index, dtype=np.uint64)
+    idx = rows[:, None] * np.uint64(components)
     comp = np.arange(components, dtype=np.uint64)[None, :]
     with np.errstate(over="ignore"):
         key = _splitmix64(np.full((1, 1), seed, dtype=np.uint64)) ^ (idx + comp)
@@ -36,11 +38,12 @@ def u01(seed: int, n: int, components: int = 6, first: int = 0) -> np.ndarray:
 
 
 def uniform_flock(n: int, extent: float, seed: int = SEED, vel_lo: float = -1.0,
-                  vel_hi: float = 1.0, first: int = 0) -> np.ndarray:
+                  vel_hi: float = 1.0, first: int = 0, index=None) -> np.ndarray:
     """Positions U[0, extent)^3, velocities U[vel_lo, vel_hi)^3 -> ``[n, 6]`` float32
     (configs C2-C5).  ``first`` offsets the boid index so ranks can generate
-    disjoint pieces of one global flock."""
-    u = u01(seed, n, 6, first)
+    disjoint pieces of one global flock; ``index`` asks for the rows of given boids."""
+    u = u01(seed, n, 6, first, index)
+    n = len(u)
     s = np.empty((n, 6), dtype=np.float32)
     s[:, :3] = u[:, :3] * np.float32(extent)
     s[:, 3:] = np.float32(vel_lo) + u[:, 3:] * np.float32(vel_hi - vel_lo)

@@ -207,6 +207,36 @@ int fp_state_euler_combine(int device, size_t n, const float *s, const float *ds
 int fp_state_rk4_combine(int device, size_t n, const float *s, const float *k1, const float *k2,
                          const float *k3, const float *k4, float h, float *out);
 
+/* Device-resident State<T> (src/simulation/state.rs:37-113) for the reference's Stateful types
+ * (state.rs:10-16).  The flat state vector -- State::as_vector, n x num_state_elements floats in
+ * the element order of each type's as_state -- lives on the device between steps; a step is one
+ * streaming pass in which every element evaluates all stages of the integrator in registers
+ * (Stateful::derivative sees only its own element, state.rs:14), 2 x 4 bytes of HBM traffic per
+ * float and step.  Same arithmetic, operation for operation, as State::euler_step / rk4_step. */
+enum {
+    FP_STATEFUL_TEST_POINT = 1,     /* state.rs:120-152: [p3 v3], derivative [v, (1, -1, 0)]          */
+    FP_STATEFUL_TEST_EXAMPLEFN = 2, /* state.rs:187-216: [y t timestep], y' = y - t^2 + 1              */
+    FP_STATEFUL_SPRINGY_POINT = 3,  /* springy_mesh.rs:199-257: [mass p3 v3 accumulated_force3]        */
+    FP_STATEFUL_RIGIDBODY = 4,      /* rigidbody.rs:53-190: [p3 q(v3 s) P3 L3 mass Iinv0(9) F3 T3]     */
+    FP_STATEFUL_BOID = 5            /* [p3 v3 a3]: a FlockingBoid with its acceleration frozen         */
+};
+typedef struct fp_state fp_state;
+int fp_state_num_state_elements(int kind);                 /* Stateful::num_state_elements (0: unknown kind) */
+/* State::new / State::from_state_vector: state = n_elements x k floats (NULL: zeros) */
+int fp_state_create(fp_state **out, int device, int kind, uint64_t n_elements, const float *state);
+int fp_state_destroy(fp_state *s);
+uint64_t fp_state_len(const fp_state *s);
+int fp_state_write(fp_state *s, const float *state);       /* from_state_vector */
+int fp_state_read(fp_state *s, float *out);                /* as_vector / get_elements */
+int fp_state_derivative(fp_state *s, float *out);          /* State::derivative */
+/* nsteps x State::euler_step(h) / State::rk4_step(h); asynchronous on the handle's stream */
+int fp_state_euler_step(fp_state *s, float h, uint32_t nsteps);
+int fp_state_rk4_step(fp_state *s, float h, uint32_t nsteps);
+int fp_state_sync(fp_state *s);
+int fp_state_device_vector(fp_state *s, const float **dev); /* valid until the next step */
+/* bench hook: `launches` single-step passes timed with CUDA events on the handle's stream */
+int fp_state_time_steps(fp_state *s, float h, int rk4, uint32_t launches, float *ms_total);
+
 /* Multi-GPU (one process per GPU).  The flock is sharded by boid index
  * (all-pairs: NCCL all-gather of pos/vel each step) or by x-slab (grid: halo
  * exchange + migration).  nccl_unique_id is the 128-byte ncclUniqueId made by

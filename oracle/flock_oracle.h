@@ -145,6 +145,17 @@ void orc_state_rk4(const float *s, size_t n, float h, orc_deriv_fn deriv, void *
 void orc_deriv_test_point(const float *s, float *ds, size_t n, void *ctx);
 void orc_deriv_test_examplefn(const float *s, float *ds, size_t n, void *ctx);
 
+/* next_oracle.c -- SURVEY 8(f) rows.  Stateful::derivative of the reference's element types:
+ * springy Point (10 floats, springy_mesh.rs:199-257), rigid-body State (29 floats,
+ * rigidbody.rs:53-190), and a boid with frozen acceleration (9 floats). */
+void orc_deriv_springy_point(const float *s, float *ds, size_t n, void *ctx);
+void orc_deriv_rigidbody(const float *s, float *ds, size_t n, void *ctx);
+void orc_deriv_boid(const float *s, float *ds, size_t n, void *ctx);
+/* sph/mod.rs:89-121: k nearest within kernal_max_distance (ascending distance, ties by id) and the
+ * Monaghan density; out_index n x k (0xffffffff beyond out_count). */
+void orc_sph_neighbors(uint64_t n, const float *pos3, uint32_t k, float s, float mass, uint32_t *out_index,
+                       uint32_t *out_count, float *out_density);
+
 /* Largest c in [-1,1] with acosf(c) > theta (this libm); -2.0f if none.
  * Used by tests to check the GPU library's threshold form of the FOV test. */
 float orc_acos_threshold(float theta);

@@ -53,7 +53,7 @@ DERIV_FN = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_siz
 
 
 def build_oracle(force: bool = False) -> str:
-    src = [os.path.join(ORACLE_DIR, f) for f in ("flock_oracle.c", "flock_oracle.h", "Makefile")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("flock_oracle.c", "next_oracle.c", "flock_oracle.h", "Makefile")]
     stale = (not os.path.exists(ORACLE_SO)) or any(
         os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in src)
     if force or stale:
@@ -302,7 +302,8 @@ class Oracle:
     # ---- State ----------------------------------------------------------
     def _deriv(self, deriv):
         if isinstance(deriv, str):
-            fn = getattr(self.lib, "orc_deriv_test_" + deriv)
+            fn = getattr(self.lib, "orc_deriv_" + deriv if hasattr(self.lib, "orc_deriv_" + deriv)
+                         else "orc_deriv_test_" + deriv)
             return C.cast(fn, C.c_void_p), None
         def _cb(s, ds, n, ctx):
             sv = np.ctypeslib.as_array(s, shape=(n,))
@@ -325,6 +326,18 @@ class Oracle:
         fn, keep = self._deriv(deriv)
         self.lib.orc_state_rk4(_ptr(s), s.size, h, fn, None, _ptr(out))
         return out
+
+    def sph_neighbors(self, pos3, k=8, s=0.1, mass=0.001):
+        """sph/mod.rs:89-121 -> (index [n, k], count [n], density [n])"""
+        p = _f32(pos3).reshape(-1, 3)
+        n = len(p)
+        idx = np.zeros((n, k), np.uint32)
+        cnt = np.zeros(n, np.uint32)
+        den = np.zeros(n, np.float32)
+        self.lib.orc_sph_neighbors.argtypes = [C.c_uint64, C.c_void_p, C.c_uint32, C.c_float, C.c_float,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.orc_sph_neighbors(n, _ptr(p), k, s, mass, _ptr(idx), _ptr(cnt), _ptr(den))
+        return idx, cnt, den
 
     # ---- misc -----------------------------------------------------------
     def acos_threshold(self, theta: float) -> float:

@@ -102,7 +102,17 @@ def test_c2_hundred_thousand_boids_allpairs_literal_rows(orc, numerics):
         if numerics == "exact":
             assert np.array_equal(ga[lo:hi].view(np.uint32), ra.view(np.uint32))   # same order, same bits
         else:
-            assert rel_err(ga[lo:hi], ra) <= ACC_RTOL
+            # With ~45 000 in-range neighbours per boid the reference's own f32 sum moves by more than
+            # 1e-5 when its loop order changes (measured here: the same rows with the other boids
+            # listed in reverse).  FAST sums in another order again (j split across lanes); the bar is
+            # the north star's 1e-5 or twice the reference's own order sensitivity, whichever is larger.
+            perm = np.concatenate([np.arange(lo, hi), np.arange(lo - 1, -1, -1), np.arange(n - 1, hi - 1, -1)])
+            rb, _, _ = orc.accel_rows(c, sc, st[perm], 0, hi - lo, threads=NT)
+            noise = rel_err(rb, ra)
+            err = rel_err(ga[lo:hi], ra)
+            print(f"C2 fast rows {lo}:{hi}: err {err:.2e}, reference order sensitivity {noise:.2e}")
+            assert err <= max(ACC_RTOL, 2.0 * noise), (err, noise)
+            assert err <= 1e-4
     assert 20000 < gc.mean() < 60000          # dense: tens of thousands of in-range neighbours each
     sim.step_many(3)
     cur = st
