@@ -237,6 +237,17 @@ int fp_state_device_vector(fp_state *s, const float **dev); /* valid until the n
 /* bench hook: `launches` single-step passes timed with CUDA events on the handle's stream */
 int fp_state_time_steps(fp_state *s, float h, int rk4, uint32_t launches, float *ms_total);
 
+/* The neighbour pass of sph::Simulation::step (src/simulation/sph/mod.rs:89-121) on the flocking
+ * path's grid infrastructure (cell keys, radix sort, cell table) instead of a kd-tree rebuilt every
+ * step: for every particle its k nearest (itself included, ascending squared_euclidean distance;
+ * equal distances by particle id -- declared, kiddo leaves it unspecified) closer than
+ * kernal_max_distance, and the density sum(particle_mass * monaghan(r, s)) over them in that order
+ * (kernals.rs:6-16).  pos3: n x 3 (host); out_index: n x k particle ids, 0xffffffff past out_count[i].
+ * 1 <= k <= 32.  kernel_ms (may be NULL): device time of binning + query. */
+int fp_sph_neighbors(int device, uint64_t n, const float *pos3, uint32_t k, float kernal_max_distance,
+                     float particle_mass, uint32_t *out_index, uint32_t *out_count, float *out_density,
+                     float *kernel_ms);
+
 /* Multi-GPU (one process per GPU).  The flock is sharded by boid index
  * (all-pairs: NCCL all-gather of pos/vel each step) or by x-slab (grid: halo
  * exchange + migration).  nccl_unique_id is the 128-byte ncclUniqueId made by

@@ -1,11 +1,24 @@
 // build.rs -- compiles the CUDA sources for sm_100a with nvcc and links the result.
 // (feriphys's own build.rs only copies assets, build.rs:1-18; this one has no ancestor.)
-use std::{env, path::PathBuf, process::Command};
+//
+// The list of translation units is READ from feriphys_b200/csrc/Makefile (its SRCS line), so the
+// crate and the in-tree build cannot drift apart (tests/test_rust_crate.py checks the parse).
+use std::{env, fs, path::PathBuf, process::Command};
 
-const SOURCES: &[&str] = &[
-    "fp_api.cu", "fp_allpairs.cu", "fp_small.cu", "fp_grid.cu", "fp_walk.cu", "fp_sort.cu",
-    "fp_misc.cu", "fp_shard.cu",
-];
+fn makefile_sources(makefile: &str) -> Vec<String> {
+    let text = fs::read_to_string(makefile).expect("cannot read feriphys_b200/csrc/Makefile");
+    let line = text
+        .lines()
+        .find(|l| l.trim_start().starts_with("SRCS"))
+        .expect("no SRCS line in the Makefile");
+    line.split_once('=')
+        .expect("malformed SRCS line")
+        .1
+        .split_whitespace()
+        .filter(|w| w.ends_with(".cu"))
+        .map(str::to_owned)
+        .collect()
+}
 
 fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
@@ -16,14 +29,27 @@ fn main() {
         return;
     }
     // repository layout: <root>/rust/feriphys-cuda/build.rs, <root>/feriphys_b200/csrc/*.cu
-    let csrc = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../../feriphys_b200/csrc");
+    let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../..");
+    let csrc = root.join("feriphys_b200/csrc");
+    let makefile = csrc.join("Makefile");
+    println!("cargo:rerun-if-changed={}", makefile.display());
+    let sources = makefile_sources(makefile.to_str().unwrap());
+    assert!(!sources.is_empty(), "the Makefile lists no .cu sources");
+    // every header the translation units include
+    for entry in fs::read_dir(&csrc).unwrap().flatten() {
+        let p = entry.path();
+        if matches!(p.extension().and_then(|e| e.to_str()), Some("cuh") | Some("h")) {
+            println!("cargo:rerun-if-changed={}", p.display());
+        }
+    }
+    println!("cargo:rerun-if-changed={}", root.join("include/feriphys_cuda.h").display());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     let lib = out.join("libferiphys_cuda.so");
     let mut cmd = Command::new(nvcc);
     cmd.args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--cudart", "static", "-shared", "-Xcompiler", "-fPIC", "-o"])
         .arg(&lib);
-    for s in SOURCES {
+    for s in &sources {
         let p = csrc.join(s);
         println!("cargo:rerun-if-changed={}", p.display());
         cmd.arg(p);

@@ -6,8 +6,10 @@
 //! equivalents of the host logic below are `cpp/feriphys_cuda.hpp` and
 //! `feriphys_b200/flocking.py`.
 pub mod ffi;
+pub mod state;
 
 use cgmath::{Quaternion, Vector3, Zero};
+use state::Stateful;
 use std::{ffi::CStr, ptr, time::Duration};
 
 /// flocking::Config (flocking.rs:15-51), field for field.
@@ -121,6 +123,41 @@ pub struct Instance {
     pub scale: f32,
 }
 
+/// boid.rs:56-64 with the acceleration of the step carried as frozen state -- the pattern of the
+/// reference's own Stateful types (springy_mesh.rs:199-257): `[p, v, a]`, derivative `[v, a, 0]`.
+#[derive(Clone, Copy, Debug, PartialEq)]
+pub struct FlockingBoid {
+    pub position: Vector3<f32>,
+    pub velocity: Vector3<f32>,
+    pub acceleration: Vector3<f32>,
+}
+impl Stateful for FlockingBoid {
+    fn num_state_elements() -> usize {
+        9
+    }
+    fn from_state_vector(s: Vec<f32>) -> Self {
+        if s.len() != Self::num_state_elements() {
+            panic!("State Vector incorrect size!")
+        }
+        FlockingBoid {
+            position: Vector3::new(s[0], s[1], s[2]),
+            velocity: Vector3::new(s[3], s[4], s[5]),
+            acceleration: Vector3::new(s[6], s[7], s[8]),
+        }
+    }
+    fn derivative(&self) -> Vec<f32> {
+        vec![self.velocity.x, self.velocity.y, self.velocity.z, self.acceleration.x, self.acceleration.y,
+             self.acceleration.z, 0.0, 0.0, 0.0]
+    }
+    fn as_state(&self) -> Vec<f32> {
+        vec![self.position.x, self.position.y, self.position.z, self.velocity.x, self.velocity.y, self.velocity.z,
+             self.acceleration.x, self.acceleration.y, self.acceleration.z]
+    }
+    fn device_kind() -> Option<i32> {
+        Some(ffi::FP_STATEFUL_BOID)
+    }
+}
+
 fn check(rc: i32) {
     if rc != ffi::FP_OK {
         // the reference's failure mode is panic!/unwrap
@@ -155,7 +192,7 @@ impl Simulation {
                 state.extend([jitter(), jitter(), jitter()]);
             }
         }
-        Self::from_state(state, bounding_box, lead_boids, obstacles, attractors)
+        Self::from_state(state, bounding_box, lead_boids, obstacles, attractors, 0)
     }
 
     /// ADDITION: explicit state, `[px py pz vx vy vz]` per boid.
@@ -165,12 +202,13 @@ impl Simulation {
         lead_boids: Option<Vec<LeadBoid>>,
         obstacles: Option<Vec<Obstacle>>,
         attractors: Option<Vec<PointAttractor>>,
+        device: i32, // CUDA ordinal
     ) -> Simulation {
         let config = Config::default();
         let n = state.len() / 6;
         let mut handle = ptr::null_mut();
         let c = config.to_c();
-        check(unsafe { ffi::fp_flock_create(&mut handle, &c, n as u64, state.as_ptr(), 0) });
+        check(unsafe { ffi::fp_flock_create(&mut handle, &c, n as u64, state.as_ptr(), device) });
         if let Some(b) = &bounding_box {
             let r = [b.x_range.start, b.x_range.end, b.y_range.start, b.y_range.end, b.z_range.start, b.z_range.end];
             check(unsafe { ffi::fp_flock_set_bbox(handle, r.as_ptr()) });
@@ -230,6 +268,22 @@ impl Simulation {
                 scale: r[7],
             })
             .collect()
+    }
+
+    /// ADDITION: `FP_NUMERICS_EXACT` / `FP_NUMERICS_FAST` (include/feriphys_cuda.h)
+    pub fn set_numerics(&mut self, numerics: i32) {
+        check(unsafe { ffi::fp_flock_set_numerics(self.handle, numerics) });
+    }
+
+    /// ADDITION: the flock as `State<FlockingBoid>` advanced by `State::euler_step(h)` /
+    /// `State::rk4_step(h)` (state.rs:75-106) with this step's accelerations frozen, device-resident.
+    pub fn state_step(&mut self, integration: state::Integration, h: f32) {
+        check(unsafe {
+            match integration {
+                state::Integration::Euler => ffi::fp_flock_state_euler(self.handle, h),
+                state::Integration::Rk4 => ffi::fp_flock_state_rk4(self.handle, h),
+            }
+        });
     }
 
     /// ADDITION
