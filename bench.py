@@ -62,8 +62,10 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="cpu_baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--numerics", default=None, choices=["exact", "fast"],
-                    help="arithmetic of the forces (default: the library's default)")
+    ap.add_argument("--numerics", default="fast", choices=["exact", "fast"],
+                    help="arithmetic of the forces: fast (default here; the north star's own bars: neighbour sets "
+                         "bit-exact, accelerations within 1e-5) or exact (the library's default: every operation "
+                         "separately rounded); the other one is measured beside it (other_numerics)")
     ap.add_argument("--no-alt", action="store_true", help="skip the comparison run with the other numerics")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled parity check against the oracle")
     return ap.parse_args()

@@ -401,6 +401,7 @@ allpairs_fast_kernel(const DevParams P, const float4 *__restrict__ pos_all, cons
         b[k].ax = b[k].ay = b[k].az = 0.0f;
     }
     const bool need_pairs = (TAP != TAP_STEP) || !P.steering_overrides;
+    bool dense = false;
     if (need_pairs) {
         for (uint32_t j0 = 0; j0 < n_all; j0 += APF_TJ) {
             __syncthreads();  // everyone is done with the previous tile
@@ -420,23 +421,28 @@ allpairs_fast_kernel(const DevParams P, const float4 *__restrict__ pos_all, cons
             }
             __syncthreads();
             const uint32_t cnt = min((uint32_t)APF_TJ, n_all - j0);
+            uint32_t tried = 0, hits = 0;
             for (uint32_t q = slice; 4u * q < cnt; q += JS) {
-                const float4 X = *reinterpret_cast<const float4 *>(&S.xc[4 * q]);
-                const float4 Y = *reinterpret_cast<const float4 *>(&S.yc[4 * q]);
-                const float4 Z = *reinterpret_cast<const float4 *>(&S.zc[4 * q]);
-                const float4 W = *reinterpret_cast<const float4 *>(&S.w[4 * q]);
-                const float2 X01 = make_float2(X.x, X.y), X23 = make_float2(X.z, X.w);
-                const float2 Y01 = make_float2(Y.x, Y.y), Y23 = make_float2(Y.z, Y.w);
-                const float2 Z01 = make_float2(Z.x, Z.y), Z23 = make_float2(Z.z, Z.w);
-                const float2 W01 = make_float2(W.x, W.y), W23 = make_float2(W.z, W.w);
-                bool hit = false;
+                bool hit = dense;
+                if (!dense) {
+                    const float4 X = *reinterpret_cast<const float4 *>(&S.xc[4 * q]);
+                    const float4 Y = *reinterpret_cast<const float4 *>(&S.yc[4 * q]);
+                    const float4 Z = *reinterpret_cast<const float4 *>(&S.zc[4 * q]);
+                    const float4 W = *reinterpret_cast<const float4 *>(&S.w[4 * q]);
+                    const float2 X01 = make_float2(X.x, X.y), X23 = make_float2(X.z, X.w);
+                    const float2 Y01 = make_float2(Y.x, Y.y), Y23 = make_float2(Y.z, Y.w);
+                    const float2 Z01 = make_float2(Z.x, Z.y), Z23 = make_float2(Z.z, Z.w);
+                    const float2 W01 = make_float2(W.x, W.y), W23 = make_float2(W.z, W.w);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const float2 t01 = __ffma2_rn(b[k].ax2, X01, __ffma2_rn(b[k].ay2, Y01, __ffma2_rn(b[k].az2, Z01, W01)));
-                    const float2 t23 = __ffma2_rn(b[k].ax2, X23, __ffma2_rn(b[k].ay2, Y23, __ffma2_rn(b[k].az2, Z23, W23)));
-                    // one compare per boid and batch.  (fminf drops a NaN operand: a record with a
-                    // non-finite position can go unseen here -- FAST numerics are defined on finite states.)
-                    hit |= !(fminf(fminf(t01.x, t01.y), fminf(t23.x, t23.y)) >= b[k].thr);
+                    for (int k = 0; k < 2; ++k) {
+                        const float2 t01 = __ffma2_rn(b[k].ax2, X01, __ffma2_rn(b[k].ay2, Y01, __ffma2_rn(b[k].az2, Z01, W01)));
+                        const float2 t23 = __ffma2_rn(b[k].ax2, X23, __ffma2_rn(b[k].ay2, Y23, __ffma2_rn(b[k].az2, Z23, W23)));
+                        // one compare per boid and batch.  (fminf drops a NaN operand: a record with a
+                        // non-finite position can go unseen here -- FAST numerics are defined on finite states.)
+                        hit |= !(fminf(fminf(t01.x, t01.y), fminf(t23.x, t23.y)) >= b[k].thr);
+                    }
+                    ++tried;
+                    hits += hit ? 1u : 0u;
                 }
                 if (hit) {  // someone may be in range: the whole batch takes the exact distance test
 #pragma unroll
@@ -448,6 +454,10 @@ allpairs_fast_kernel(const DevParams P, const float4 *__restrict__ pos_all, cons
                     }
                 }
             }
+            // a dense flock (C2: half of all pairs are in range) gains nothing from the pre-gate: once
+            // most batches of a tile hit, the warp stops asking (decided once, warp-uniform)
+            if (!dense && j0 >= 4u * APF_TJ)
+                dense = __reduce_add_sync(0xffffffffu, hits) * 4u > __reduce_add_sync(0xffffffffu, tried) * 3u;
         }
     }
     // the JS partial sums of each boid -> its slice-0 lane

@@ -585,6 +585,9 @@ NlIO nl_io(const fp_flock *f, double skins = 1.0) {
     // (skins = 2: within reach + 2 skin at any other moment of the binning's life)
     const double R = (double)reach_of(f->cfg) + skins * (double)f->grid.skin;
     nl.m2_wide = nextafterf((float)(R * R * (1.0 + 1e-5)), INFINITY);
+    // the fast walk sums in list order whatever it is: its lists put the entries in view first
+    nl.vis_first = f->P.numerics_fast && f->P.fz_a > -2.5f && f->P.fz_a < 1.0f ? 1 : 0;
+    nl.vis_c = f->P.fz_a;
     return nl;
 }
 
@@ -941,6 +944,10 @@ int fp_flock_destroy(fp_flock *f) {
     free_grid_work(f);
     nl_free(f);
     if (f->d_stage) cudaFree(f->d_stage);
+    for (int k = 0; k < 2; ++k) {
+        if (f->h_up[k]) cudaFreeHost(f->h_up[k]);
+        if (f->up_ev[k]) cudaEventDestroy(f->up_ev[k]);
+    }
     if (f->h_ctl) cudaFreeHost(f->h_ctl);
     for (auto &ev : f->ev_pool) if (ev) cudaEventDestroy(ev);
     for (auto &ev : f->ap_ev) if (ev) cudaEventDestroy(ev);
@@ -1290,11 +1297,25 @@ int fp_flock_write_state(fp_flock *f, const float *state) {
     if (!state) { set_error("null state"); return FP_ERR_INVALID; }
     const size_t bytes = (size_t)f->n * 6 * sizeof(float);
     if ((rc = ensure_stage(f, bytes))) return rc;
-    FP_CUDA(cudaMemcpyAsync(f->d_stage, state, bytes, cudaMemcpyHostToDevice, f->stream));
+    const bool small = bytes <= fp_flock::SMALL_UPLOAD;
+    const void *src = state;
+    uint32_t slot = 0;
+    if (small) {  // copy the caller's buffer out now; the device picks it up when it gets there
+        slot = f->up_cur++ & 1u;
+        if (!f->h_up[slot]) {
+            FP_CUDA(cudaMallocHost(&f->h_up[slot], fp_flock::SMALL_UPLOAD));
+            FP_CUDA(cudaEventCreateWithFlags(&f->up_ev[slot], cudaEventDisableTiming));
+        }
+        FP_CUDA(cudaEventSynchronize(f->up_ev[slot]));  // the upload that last used this slot
+        memcpy(f->h_up[slot], state, bytes);
+        src = f->h_up[slot];
+    }
+    FP_CUDA(cudaMemcpyAsync(f->d_stage, src, bytes, cudaMemcpyHostToDevice, f->stream));
     if ((rc = launch_aos6_to_soa(f->stream, (const float *)f->d_stage, f->pos[f->cur], f->vel[f->cur],
                                  f->n, f->first_index)))
         return rc;
-    FP_CUDA(cudaStreamSynchronize(f->stream));
+    if (small) FP_CUDA(cudaEventRecord(f->up_ev[slot], f->stream));
+    else FP_CUDA(cudaStreamSynchronize(f->stream));  // the caller's buffer is not retained
     f->permuted = false;
     f->bin_valid = false;
     f->nl_off = false;

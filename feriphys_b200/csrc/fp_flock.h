@@ -78,6 +78,12 @@ struct fp_flock {
     // staging for host transfers
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
+    // small uploads (demo-sized flocks) go through two pinned slots so that fp_flock_write_state
+    // can return without waiting for the device: the caller's buffer is copied out at once
+    static constexpr size_t SMALL_UPLOAD = 256 * 1024;
+    void *h_up[2] = {nullptr, nullptr};
+    cudaEvent_t up_ev[2] = {nullptr, nullptr};
+    uint32_t up_cur = 0;
     // timing hook: three events per step (before sort phase, before influence, after)
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;

@@ -171,6 +171,8 @@ struct NlIO {
     uint32_t vcap;       // list capacity, a multiple of 4
     uint32_t tile_cap;   // staged candidates the walk that will use the lists can hold per CTA
     float m2_wide;       // build cut: (reach + skin)^2 (1 + 1e-5)
+    int vis_first;       // order each list with the entries predicted to be in view first (fast walk)
+    float vis_c;         // ... in view <=> cosine of the sight angle > vis_c
 };
 size_t nl_entries_elems(uint32_t rows, uint32_t vcap);
 size_t nl_cta_tab_elems(uint32_t rows);

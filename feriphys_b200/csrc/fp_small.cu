@@ -8,6 +8,8 @@
 // Latency is hidden inside the thread: four pairs per trip are evaluated with
 // the branch-free exact pair function (independent dependency chains the
 // scheduler interleaves) and then added to the accumulator in index order.
+#include <stdlib.h>
+
 #include "fp_internal.h"
 
 namespace fp {
@@ -99,6 +101,91 @@ small_kernel(const DevParams P, float4 *__restrict__ gpos, float4 *__restrict__ 
     if (flags) atomicOr(status, flags);
 }
 
+// ---- K4, lane-parallel form for N <= 128 (the demo's 110 boids) ---------------------------------
+// The one-thread-per-boid kernel above leaves 7/8 of the SM idle and spends a step walking 110
+// dependent pair evaluations per thread.  Here the N^2 exact pair terms of a step are evaluated by
+// all 1024 threads of the CTA at once -- S2_LANES lanes per boid, lane s takes j = s, s + 8, ... --
+// and written to shared memory as c[i][j]; then one thread per boid adds its row in ascending j,
+// which is the reference's loop order (flocking.rs:136): same terms, same order, same bits.  The
+// row sum is a chain of N dependent f32 adds (~0.25 us); the pair terms, the expensive part, run
+// eight-wide.  Demo scene: 24 -> ~4 us per step.
+constexpr int S2_THREADS = 1024;
+constexpr int S2_MAX = 128;
+constexpr int S2_STRIDE = S2_MAX + 1;  // odd row stride: the row sums of 32 boids hit 32 banks
+constexpr int S2_LANES = 8;
+
+uint32_t small2_max_boids() { return S2_MAX; }
+
+struct Small2Smem {
+    float4 pos[2][S2_MAX], vel[2][S2_MAX];
+    float cx[S2_MAX * S2_STRIDE], cy[S2_MAX * S2_STRIDE], cz[S2_MAX * S2_STRIDE];
+    unsigned char valid[S2_MAX * S2_MAX];  // the pair contributes (in range and visible)
+};
+
+__global__ void __launch_bounds__(S2_THREADS, 1)
+small2_kernel(const DevParams P, float4 *__restrict__ gpos, float4 *__restrict__ gvel, uint32_t n,
+              uint32_t nsteps, const float *__restrict__ lead_table, uint32_t lead_rows,
+              unsigned *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char s2_raw[];
+    Small2Smem &S = *reinterpret_cast<Small2Smem *>(s2_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t i = tid / S2_LANES, lane = tid % S2_LANES;
+    if (tid < n) {
+        S.pos[0][tid] = gpos[tid];
+        S.vel[0][tid] = gvel[tid];
+    }
+    int cur = 0;
+    unsigned flags = 0;
+    const int lead_stride = P.n_leads * 8;
+    for (uint32_t step = 0; step < nsteps; ++step) {
+        __syncthreads();
+        const float *leads = lead_table ? lead_table + (size_t)min(step, lead_rows - 1) * lead_stride : P.leads;
+        if (i < n && !P.steering_overrides) {
+            const float4 pi4 = S.pos[cur][i], vi4 = S.vel[cur][i];
+            const Self self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
+            for (uint32_t j = lane; j < n; j += S2_LANES) {
+                const float4 pj = S.pos[cur][j];
+                V3 d, c = v3zero();
+                const float m2 = pair_m2(self, v3(pj.x, pj.y, pj.z), d);
+                bool ok = false;
+                if (!(m2 >= P.m2_cut)) {
+                    const float4 vj = S.vel[cur][j];
+                    ok = pair_flock(P, self, d, m2, v3(vj.x, vj.y, vj.z), c);
+                }
+                S.cx[i * S2_STRIDE + j] = c.x;
+                S.cy[i * S2_STRIDE + j] = c.y;
+                S.cz[i * S2_STRIDE + j] = c.z;
+                S.valid[i * S2_MAX + j] = ok ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        if (tid < n) {
+            const float4 pi4 = S.pos[cur][tid], vi4 = S.vel[cur][tid];
+            const Self self = make_self(v3(pi4.x, pi4.y, pi4.z), v3(vi4.x, vi4.y, vi4.z));
+            V3 acc = v3zero();
+            if (!P.steering_overrides) {
+                const float *rx = S.cx + tid * S2_STRIDE, *ry = S.cy + tid * S2_STRIDE, *rz = S.cz + tid * S2_STRIDE;
+                const unsigned char *rv = S.valid + tid * S2_MAX;
+                for (uint32_t j = 0; j < n; ++j)
+                    if (rv[j]) acc = vadd(acc, v3(rx[j], ry[j], rz[j]));  // ascending j: the reference's order
+            }
+            Extras e;
+            const V3 a = accel_total(P, self, acc, e, flags, false, leads);
+            V3 np, nv;
+            euler(P, self.p, self.v, a, np, nv);
+            S.pos[cur ^ 1][tid] = make_float4(np.x, np.y, np.z, pi4.w);
+            S.vel[cur ^ 1][tid] = make_float4(nv.x, nv.y, nv.z, 0.0f);
+        }
+        cur ^= 1;
+    }
+    __syncthreads();
+    if (tid < n) {
+        gpos[tid] = S.pos[cur][tid];
+        gvel[tid] = S.vel[cur][tid];
+    }
+    if (flags) atomicOr(status, flags);
+}
+
 int launch_small(cudaStream_t st, const DevParams &P, float4 *pos, float4 *vel, uint32_t n,
                  uint32_t nsteps, const float *lead_table, uint32_t lead_rows, unsigned *status) {
     if (!n || !nsteps) return FP_OK;
@@ -106,8 +193,19 @@ int launch_small(cudaStream_t st, const DevParams &P, float4 *pos, float4 *vel, 
         set_error("flock too large for the single-CTA kernel");
         return FP_ERR_INVALID;
     }
-    small_kernel<<<1, SM_THREADS, 0, st>>>(P, pos, vel, n, nsteps, lead_rows ? lead_table : nullptr, lead_rows,
-                                          status);
+    static const bool lane_parallel = [] {  // FP_SMALL_VARIANT=1: the one-thread-per-boid kernel (cross-check)
+        const char *e = getenv("FP_SMALL_VARIANT");
+        return !(e && *e == '1');
+    }();
+    if (n <= S2_MAX && lane_parallel) {
+        const int smem = (int)sizeof(Small2Smem);
+        FP_CUDA(cudaFuncSetAttribute(small2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        small2_kernel<<<1, S2_THREADS, smem, st>>>(P, pos, vel, n, nsteps, lead_rows ? lead_table : nullptr, lead_rows,
+                                                  status);
+    } else {
+        small_kernel<<<1, SM_THREADS, 0, st>>>(P, pos, vel, n, nsteps, lead_rows ? lead_table : nullptr, lead_rows,
+                                              status);
+    }
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;

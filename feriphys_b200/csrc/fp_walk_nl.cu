@@ -20,7 +20,11 @@
 //       exact squared distance (so the distance decisions are the reference's), the field-of-view
 //       decision on a fused cosine outside a 1e-5 guard band and by the exact sequence inside it,
 //       forces with FMA and MUFU.RSQ.  Neighbour sets are bit-exact, accelerations agree with the
-//       reference to ~1e-6 relative (bar: 1e-5); the summation order is still the list order.
+//       reference to ~1e-6 relative (bar: 1e-5).  Its lists are built VISIBLE FIRST: the entries the
+//       boid is predicted to see (field of view at build time) come before the ones it is not, so a
+//       warp's lanes agree far more often on whether an entry contributes -- the force code runs for
+//       the first ~half of the rows with most lanes active and is skipped for the rest (in slot
+//       order it ran on every row with a third of the lanes: profiles/r2_c4_nl_fast_v1_*).
 //
 // Exactness of the lists.  While the binning stands every boid is within skin / 2 of where it was
 // binned (the device-checked displacement bound D), so a pair closer than reach now was closer
@@ -119,6 +123,13 @@ struct NlBuildSmem {
     alignas(8) uint64_t bar;
 };
 
+constexpr int NB_TMP = 64;  // VIS_FIRST: entries held back in shared memory (the ones not in view)
+
+// VIS_FIRST (the fast walk's lists): entries the boid is predicted to SEE -- fused cosine of the
+// sight angle against nl.vis_c, from the velocities of this moment -- are written first, the others
+// after them (each class in ascending slot order).  Any order is a correct list; this one makes the
+// lanes of a warp agree on whether row k contributes.
+template <bool VIS_FIRST>
 __global__ void __launch_bounds__(NL_BLOCK)
 nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     // (No look at ctl->stale: the lists describe the binning, which stands whether or not the
@@ -140,9 +151,17 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     float4 pi4 = make_float4(0, 0, 0, 0);
     bool work = false;
     int cx = 0, cy = 0, cz = 0;
+    float2 vhx = make_float2(0, 0), vhy = vhx, vhz = vhx;  // VIS_FIRST: direction of flight, both halves
     if (active) {
         pi4 = io.pos_s[s];
-        work = __float_as_uint(io.vel_s[s].w) == 0u;  // not a ghost record
+        const float4 vi4 = io.vel_s[s];
+        work = __float_as_uint(vi4.w) == 0u;  // not a ghost record
+        if (VIS_FIRST) {
+            const float inv = rsqrtf(fmaf(vi4.z, vi4.z, fmaf(vi4.y, vi4.y, vi4.x * vi4.x)));  // (a prediction)
+            vhx = make_float2(vi4.x * inv, vi4.x * inv);
+            vhy = make_float2(vi4.y * inv, vi4.y * inv);
+            vhz = make_float2(vi4.z * inv, vi4.z * inv);
+        }
         home_cell(g, __ldg(io.home + (s - io.first)), cx, cy, cz);
     }
     // the nine slot ranges of this boid, rows in ascending key order (dx outer, dy inner)
@@ -203,8 +222,11 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     const uint32_t t_self = work ? s - S.tslot[4] : 0xffffu;  // tile offset of the boid itself (row 4)
     if (total > 0) mbar_wait(&S.bar, 0);
     uint16_t *const out = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + tid;  // entry k at out[k * BLOCK]
+    uint16_t *const tmp = reinterpret_cast<uint16_t *>(smem_raw + sizeof(NlBuildSmem)) + tid;  // VIS_FIRST: [NB_TMP][BLOCK]
     const uint32_t vcap = nl.vcap;
-    uint32_t w = 0;  // entries found
+    uint32_t w = 0;   // entries written to the list
+    uint32_t wn = 0;  // VIS_FIRST: entries held back (not in view)
+    const float vis_c = nl.vis_c;
     const float2 nsx = make_float2(-pi4.x, -pi4.x), nsy = make_float2(-pi4.y, -pi4.y),
                  nsz = make_float2(-pi4.z, -pi4.z);
 #pragma unroll 1
@@ -227,11 +249,26 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
             const float2 m01 = __ffma2_rn(dz01, dz01, __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01)));
             const float2 m23 = __ffma2_rn(dz23, dz23, __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23)));
             const float mm[4] = {m01.x, m01.y, m23.x, m23.y};
+            float qq[4] = {0, 0, 0, 0};
+            if (VIS_FIRST) {
+                const float2 q01 = __ffma2_rn(vhz, dz01, __ffma2_rn(vhy, dy01, __fmul2_rn(vhx, dx01)));
+                const float2 q23 = __ffma2_rn(vhz, dz23, __ffma2_rn(vhy, dy23, __fmul2_rn(vhx, dx23)));
+                qq[0] = q01.x; qq[1] = q01.y; qq[2] = q23.x; qq[3] = q23.y;
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if ((live >> u & 1u) && !(mm[u] >= nl.m2_wide) && T + u != t_self) {  // NaN never drops
-                    if (w < vcap) out[(size_t)w * NL_BLOCK] = (uint16_t)(tag | (T + u));
-                    ++w;
+                    const uint16_t e = (uint16_t)(tag | (T + u));
+                    // in view <=> cos > vis_c <=> q > vis_c |d|  (q |q| against vis_c |vis_c| m2: no square root)
+                    const bool held = VIS_FIRST && wn < (uint32_t)NB_TMP &&
+                                      qq[u] * fabsf(qq[u]) <= vis_c * fabsf(vis_c) * mm[u];
+                    if (held) {
+                        tmp[(size_t)wn * NL_BLOCK] = e;
+                        ++wn;
+                    } else {
+                        if (w < vcap) out[(size_t)w * NL_BLOCK] = e;
+                        ++w;
+                    }
                 }
         };
         if (len) {
@@ -243,6 +280,12 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
             }
             for (; T + 4 <= B; T += 4) gate4(T, 0xfu);
             if (T < B) gate4(T, (1u << (B - T)) - 1u);
+        }
+    }
+    if (VIS_FIRST) {  // the entries not in view, behind the ones in view
+        for (uint32_t k = 0; k < wn; ++k) {
+            if (w < vcap) out[(size_t)w * NL_BLOCK] = tmp[(size_t)k * NL_BLOCK];
+            ++w;
         }
     }
     if (active) nl.count[s - io.first] = (uint16_t)min(w, vcap);
@@ -268,7 +311,14 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     const uint32_t tid = threadIdx.x;
     const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
     const bool active = s < io.last;
-    if (tid == 0) mbar_init(&S.bar, 1);
+    const uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
+    const bool no_lists = __ldg(tab + 18) != 0u;
+    if (tid < 32 && !no_lists) {  // warp 0 gets the tile moving before anything else
+        if (tid == 0) mbar_init(&S.bar, 1);
+        __syncwarp();
+        const uint32_t ub = tid < 9 ? __ldg(tab + tid) : 0u, ue = tid < 9 ? __ldg(tab + 9 + tid) : 0u;
+        nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], NL_TILE);
+    }
 
     float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
     uint32_t n_c = 0;  // cached candidates of this boid
@@ -291,20 +341,14 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
         work = !ghost && !P.steering_overrides;
     }
     if (!work) n_c = 0;
-    const uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
     V3 acc = v3zero();
-    if (__ldg(tab + 18)) {
+    if (no_lists) {
         // a CTA without lists (tile or list overflow at build time)
         if (work) acc = nl_walk_global(P, g, io, s, self);
         if (active) walk_finish<TAP_STEP>(P, s, pi4, vi4, self, acc, 0u, 0ull, io, status, TapOut{});
         return;
     }
-    __syncthreads();  // the barrier is initialised
-    if (tid < 32) {
-        const uint32_t ub = tid < 9 ? __ldg(tab + tid) : 0u, ue = tid < 9 ? __ldg(tab + 9 + tid) : 0u;
-        nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], NL_TILE);
-    }
-    __syncthreads();
+    __syncthreads();  // the barrier is initialised, the layout is in shared memory
     const uint32_t t_self = work ? s - S.tslot[4] : 0xffffu;
     const uint32_t nmax = __reduce_max_sync(0xffffffffu, n_c);
     if (S.toff[9] > 0) mbar_wait(&S.bar, 0);  // (a layout with lists always fits the tile)
@@ -364,87 +408,59 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
 }
 
 // ---- FAST numerics ----------------------------------------------------------------------------
-constexpr int NF_CAP = 32;  // survivor list (shared memory); a fuller list is drained mid-way
-
 struct NlFastSmem {
     alignas(16) float tx[NF_TILE + 8], ty[NF_TILE + 8], tz[NF_TILE + 8];
     alignas(16) float4 tv[NF_TILE];  // velocities of the staged candidates (.w: record flag, unused)
-    uint16_t list[NF_CAP][NL_BLOCK];  // per-thread survivors: tile offset | 0x8000 if the exact sequence must decide
     uint32_t toff[10], tslot[9];
-    alignas(8) uint64_t bar, bar_v;   // positions / velocities have landed
+    alignas(8) uint64_t bar;
 };
 
 // One entry of a boid's cached list under FAST numerics.  The squared distance is the reference's
 // own (separately rounded, boid.rs:94-96 through cgmath's dot), so "in range" and "weight 1" are its
 // decisions.  The cosine of the sight angle is fused and uses MUFU.RSQ: within ~1e-6 of the
 // reference's (boid.rs:102-105); the decision is taken on it when it is further than the guard band
-// from both ends of the culled interval [-1, cstar], else the pair goes down the exact path.
-// -> 0: no contribution, 1: contributes, 2: the exact sequence must decide
-__device__ __forceinline__ int fast_gate(const DevParams &P, const Self &self, float px, float py, float pz) {
-    const float dx = fsub(px, self.p.x), dy = fsub(py, self.p.y), dz = fsub(pz, self.p.z);
-    const float m2 = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
-    const float q = fmaf(self.vhat.z, dz, fmaf(self.vhat.y, dy, self.vhat.x * dx));
-    const float c = q * rsqrt_seed(m2);
+// from both ends of the culled interval [-1, cstar], else `unsure` sends the pair down the exact path.
+struct FastPair {
+    float dx, dy, dz, m2, r;
+    bool pass;    // contributes, decided outside the guard bands
+    bool unsure;  // in range but degenerate or inside a guard band: the exact sequence decides
+};
+__device__ __forceinline__ FastPair fast_gate(const DevParams &P, const Self &self, float px, float py, float pz,
+                                              bool live) {
+    FastPair f;
+    f.dx = fsub(px, self.p.x);
+    f.dy = fsub(py, self.p.y);
+    f.dz = fsub(pz, self.p.z);
+    f.m2 = fadd(fadd(fmul(f.dx, f.dx), fmul(f.dy, f.dy)), fmul(f.dz, f.dz));
+    const float q = fmaf(self.vhat.z, f.dz, fmaf(self.vhat.y, f.dy, self.vhat.x * f.dx));
+    f.r = rsqrt_seed(f.m2);
+    const float c = q * f.r;
     const float gc = (c - P.fz_a) * (c - P.fz_b);   // <= 0: culled (acosf(c) > max_sight_angle)
-    if (m2 >= P.m2_cut) return 0;
+    const bool in = live && !(f.m2 >= P.m2_cut);
     // coincident positions (abs_diff_eq! guards, boid.rs:111,121), NaN, and cosines in the guard band
-    if (!(fabsf(gc) > P.fz_gc_tol) || !(m2 >= 1e-12f)) return 2;
-    return gc > 0.0f ? 1 : 0;
+    const bool clear = fabsf(gc) > P.fz_gc_tol && f.m2 >= 1e-12f;
+    f.unsure = in && !clear;
+    f.pass = in && clear && gc > 0.0f;
+    return f;
 }
-// contribution of a survivor, accumulated with FMAs: w_d ((av + ce) + vm)  (boid.rs:162-165)
-__device__ __forceinline__ void fast_force(const DevParams &P, const Self &self, float px, float py, float pz,
-                                           float4 vj, bool live, float &ax, float &ay, float &az) {
-    const float dx = fsub(px, self.p.x), dy = fsub(py, self.p.y), dz = fsub(pz, self.p.z);
-    const float m2 = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
-    const float r = rsqrt_seed(m2);
+// contribution of a pair that passed, accumulated with FMAs: w_d ((av + ce) + vm)  (boid.rs:162-165)
+__device__ __forceinline__ void fast_force(const DevParams &P, const Self &self, const FastPair &f, float4 vj,
+                                           float &ax, float &ay, float &az) {
     // dist: the seed refined to the correctly rounded square root (it enters the ramp by difference)
-    const float g0 = m2 * r, h = 0.5f * r;
-    const float mag = fmaf(fmaf(-g0, g0, m2), h, g0);
-    const float coef = fmaf(P.f_c, mag, P.neg_f_a * (r * r)) * r;  // ((-f_a / d^2) + f_c d) / d, on d
-    const float w = m2 <= P.m2_one ? 1.0f : (mag - P.thr) * P.fz_rinv_fall;  // boid.rs:152-161 (F7)
+    const float g0 = f.m2 * f.r, h = 0.5f * f.r;
+    const float mag = fmaf(fmaf(-g0, g0, f.m2), h, g0);
+    const float coef = fmaf(P.f_c, mag, P.neg_f_a * (f.r * f.r)) * f.r;  // ((-f_a / d^2) + f_c d) / d, on d
+    const float w = f.m2 <= P.m2_one ? 1.0f : (mag - P.thr) * P.fz_rinv_fall;  // boid.rs:152-161 (F7)
     const float dvx = vj.x - self.v.x, dvy = vj.y - self.v.y, dvz = vj.z - self.v.z;
     const bool vsm = fmaxf(fmaxf(fabsf(dvx), fabsf(dvy)), fabsf(dvz)) <= FP_F32_EPSILON;  // boid.rs:132
-    // (selected, not multiplied by zero: an idle lane may have evaluated its own record, m2 = 0)
-    const float cw = live ? coef * w : 0.0f, fw = (live && !vsm) ? P.f_v * w : 0.0f;
-    ax = fmaf(cw, dx, fmaf(fw, dvx, ax));
-    ay = fmaf(cw, dy, fmaf(fw, dvy, ay));
-    az = fmaf(cw, dz, fmaf(fw, dvz, az));
-}
-
-// the force phase over a thread's survivor list (two entries per trip: independent chains)
-__device__ __forceinline__ void fast_drain(const DevParams &P, const Self &self, const NlFastSmem &S,
-                                           const uint16_t *lst, int nb, int nb_warp, float &ax, float &ay, float &az) {
-#pragma unroll 1
-    for (int k = 0; k < nb_warp; k += 2) {
-        const bool la = k < nb, lb = k + 1 < nb;
-        const uint32_t ea = la ? lst[k * NL_BLOCK] : 0u, eb = lb ? lst[(k + 1) * NL_BLOCK] : 0u;
-        const uint32_t ta = ea & 0xfffu, tb = eb & 0xfffu;
-        const float4 va = S.tv[ta], vb = S.tv[tb];
-        // (an idle lane evaluates tile entry 0 with weight 0: finite data, nothing added)
-        fast_force(P, self, S.tx[ta], S.ty[ta], S.tz[ta], va, la && !(ea & 0x8000u), ax, ay, az);
-        fast_force(P, self, S.tx[tb], S.ty[tb], S.tz[tb], vb, lb && !(eb & 0x8000u), ax, ay, az);
-        if ((ea | eb) & 0x8000u) {
-            // guard band / degenerate pair (rare): the reference's own sequence decides and evaluates
-#pragma unroll 1
-            for (int u = 0; u < 2; ++u) {
-                const uint32_t e = u ? eb : ea, t = e & 0xfffu;
-                if (!(e & 0x8000u)) continue;
-                V3 d, contrib;
-                const float m2 = pair_m2(self, v3(S.tx[t], S.ty[t], S.tz[t]), d);
-                const float4 vj = S.tv[t];
-                if (!(m2 >= P.m2_cut) &&
-                    pair_inrange<false>(P, self, d, m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar, contrib)) {
-                    ax += contrib.x;
-                    ay += contrib.y;
-                    az += contrib.z;
-                }
-            }
-        }
-    }
+    const float cw = coef * w, fw = vsm ? 0.0f : P.f_v * w;
+    ax = fmaf(cw, f.dx, fmaf(fw, dvx, ax));
+    ay = fmaf(cw, f.dy, fmaf(fw, dvy, ay));
+    az = fmaf(cw, f.dz, fmaf(fw, dvz, az));
 }
 
 template <int TAP>
-__global__ void __launch_bounds__(NL_BLOCK, 4)
+__global__ void __launch_bounds__(NL_BLOCK, 5)
 nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO nl, unsigned *__restrict__ status,
                TapOut tap) {
     if (TAP == TAP_STEP && io.ctl && io.ctl->stale) return;  // lazy re-binning: this step is void
@@ -455,42 +471,13 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     const bool active = s < io.last;
     const uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
     const bool no_lists = __ldg(tab + 18) != 0u;
-    if (tid < 32 && !no_lists) {
-        // warp 0 gets the tile moving before anything else: layout from the build's record, positions
-        // on one barrier, velocities (needed only by the force phase) on a second one
-        if (tid == 0) {
-            mbar_init(&S.bar, 1);
-            mbar_init(&S.bar_v, 1);
-        }
+    if (tid < 32 && !no_lists) {  // warp 0 gets the tile moving before anything else
+        if (tid == 0) mbar_init(&S.bar, 1);
         __syncwarp();
         const uint32_t ub = tid < 9 ? __ldg(tab + tid) : 0u, ue = tid < 9 ? __ldg(tab + 9 + tid) : 0u;
-        const uint32_t len = ue - ub;
-        uint32_t inc = len;  // inclusive prefix sum over the lanes
-#pragma unroll
-        for (int off = 1; off < 16; off <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
-            if ((int)tid >= off) inc += t;
-        }
-        const uint32_t toff = inc - len, total = __shfl_sync(0xffffffffu, inc, 8);
-        if (tid < 9) {
-            S.toff[tid] = toff;
-            S.tslot[tid] = ub - toff;
-        }
-        if (tid == 0) {
-            S.toff[9] = total;
-            if (total) {
-                mbar_expect_tx(&S.bar, total * 12u);
-                mbar_expect_tx(&S.bar_v, total * 16u);
-            }
-        }
-        __syncwarp();
-        if (tid < 9 && len) {  // (a layout with lists always fits the tile: the build saw to that)
-            bulk_g2s(&S.tx[toff], io.soa_in[0] + ub, len * 4u, &S.bar);
-            bulk_g2s(&S.ty[toff], io.soa_in[1] + ub, len * 4u, &S.bar);
-            bulk_g2s(&S.tz[toff], io.soa_in[2] + ub, len * 4u, &S.bar);
-            bulk_g2s(&S.tv[toff], io.vel_s + ub, len * 16u, &S.bar_v);
-        }
+        nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], NF_TILE, S.tv, io.vel_s);
     }
+
     float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
     uint32_t n_c = 0;
     if (active) {
@@ -517,22 +504,13 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
         if (active) walk_finish<TAP, true>(P, s, pi4, vi4, self, acc, 0u, 0ull, io, status, tap);
         return;
     }
+    __syncthreads();  // the barrier is initialised, the layout is in shared memory
     const uint32_t nmax = __reduce_max_sync(0xffffffffu, n_c);
-    __syncthreads();  // the barriers are initialised, the layout is in shared memory
-    const bool staged = S.toff[9] > 0;
-    if (staged) mbar_wait(&S.bar, 0);
+    if (S.toff[9] > 0) mbar_wait(&S.bar, 0);
 
-    uint16_t *const lst = &S.list[0][tid];  // entry k at lst[k * BLOCK]
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
-    int cnt = 0;
-    bool vel_ready = !staged;
 #pragma unroll 1
     for (uint32_t k = 0; k < nmax; k += 4) {
-        if (__any_sync(0xffffffffu, cnt > NF_CAP - 4)) {  // some lane's list may not take another batch
-            if (!vel_ready) { mbar_wait(&S.bar_v, 0); vel_ready = true; }
-            fast_drain(P, self, S, lst, cnt, (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt), ax, ay, az);
-            cnt = 0;
-        }
         const uint32_t c[4] = {e0, e1, e2, e3};
         if (k + 4 < nmax) {
             e0 = __ldcs(vlp + (size_t)(k + 4) * NL_BLOCK);
@@ -540,23 +518,37 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
             e2 = __ldcs(vlp + (size_t)(k + 6) * NL_BLOCK);
             e3 = __ldcs(vlp + (size_t)(k + 7) * NL_BLOCK);
         }
-        const uint32_t rem = n_c > k ? n_c - k : 0u;  // live entries of this batch
-        int verdict[4];
+        FastPair f[4];
         uint32_t t[4];
+        const uint32_t rem = n_c > k ? n_c - k : 0u;  // live entries of this batch
+        bool any_unsure = false;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             t[u] = c[u] & 0xfffu;  // (entries past n_c hold offsets of earlier builds: inside the arrays, unused)
-            verdict[u] = fast_gate(P, self, S.tx[t[u]], S.ty[t[u]], S.tz[t[u]]);
+            f[u] = fast_gate(P, self, S.tx[t[u]], S.ty[t[u]], S.tz[t[u]], (uint32_t)u < rem);
+            any_unsure |= f[u].unsure;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if ((uint32_t)u < rem && verdict[u]) {
-                lst[cnt * NL_BLOCK] = (uint16_t)(t[u] | (verdict[u] == 2 ? 0x8000u : 0u));
-                ++cnt;
+            if (f[u].pass) fast_force(P, self, f[u], S.tv[t[u]], ax, ay, az);
+        if (any_unsure) {
+            // guard band / degenerate pair (rare): the reference's own sequence decides and evaluates
+#pragma unroll 1
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t tu = (u == 0 ? c[0] : u == 1 ? c[1] : u == 2 ? c[2] : c[3]) & 0xfffu;
+                const FastPair fu = fast_gate(P, self, S.tx[tu], S.ty[tu], S.tz[tu], u < rem);
+                if (!fu.unsure) continue;
+                const float4 vj = S.tv[tu];
+                V3 contrib;
+                if (pair_inrange<false>(P, self, v3(fu.dx, fu.dy, fu.dz), fu.m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar,
+                                        contrib)) {
+                    ax += contrib.x;
+                    ay += contrib.y;
+                    az += contrib.z;
+                }
             }
+        }
     }
-    if (!vel_ready) mbar_wait(&S.bar_v, 0);
-    fast_drain(P, self, S, lst, cnt, (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt), ax, ay, az);
     if (!active) return;
     walk_finish<TAP, true>(P, s, pi4, vi4, self, v3(ax, ay, az), 0u, 0ull, io, status, tap);
 }
@@ -575,9 +567,15 @@ uint32_t nl_tile_cap(bool fast) { return fast ? NF_TILE : NL_TILE; }
 int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl) {
     if (io.last <= io.first) return FP_OK;
     const uint32_t ctas = (io.last - io.first + NL_BLOCK - 1) / NL_BLOCK;
-    const int smem = (int)sizeof(NlBuildSmem);
-    FP_CUDA(cudaFuncSetAttribute(nl_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    nl_build_kernel<<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+    if (nl.vis_first) {
+        const int smem = (int)(sizeof(NlBuildSmem) + sizeof(uint16_t) * NB_TMP * NL_BLOCK);
+        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        nl_build_kernel<true><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+    } else {
+        const int smem = (int)sizeof(NlBuildSmem);
+        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        nl_build_kernel<false><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+    }
     count_launch();
     FP_CUDA(cudaGetLastError());
     return FP_OK;
