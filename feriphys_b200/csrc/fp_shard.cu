@@ -224,6 +224,7 @@ void shard_destroy(Shard *s) {
 
 
 int shard_world(const Shard *s) { return s->world; }
+bool shard_is_slab(const Shard *s) { return s->rep == REP_SLAB; }
 
 void shard_info(const Shard *s, int *rank, int *world, int *peer_mapped) {
     if (rank) *rank = s->rank;

@@ -28,6 +28,7 @@ int shard_method(Shard *s, int requested, const fp_config &cfg);
 int shard_reduce_bounds(Shard *s, cudaStream_t st, float lo[3], float hi[3], float *v2max);
 int shard_settle(Shard *s, fp_flock *f);
 int shard_world(const Shard *s);
+bool shard_is_slab(const Shard *s);  // the flock currently lives in x-slabs (grid partition)
 void shard_info(const Shard *s, int *rank, int *world, int *peer_mapped);
 // called by fit_grid once the GLOBAL grid is known: lay out this rank's slab
 int shard_grid_fitted(Shard *s, fp_flock *f);

@@ -9,8 +9,9 @@
 //       stages the same nine intervals as the plain walk, keeps every candidate whose squared
 //       distance is below (reach + skin)^2 (1 + 1e-5), and writes the survivors' tile offsets
 //       (16 bit, row << 12 | offset, ascending slot order, the boid itself left out) to a
-//       per-thread list in global memory, [cta][entry][thread] so that entry k of a warp is one
-//       64-byte run; also the per-boid count and the CTA's tile layout (nine intervals).
+//       per-thread list in global memory, [cta][entry / 4][thread][entry % 4]: a thread fetches four
+//       entries with one 8-byte load, a warp's batch is one 256-byte run; also the per-boid count
+//       and the CTA's tile layout (nine intervals).
 //   nl_walk_kernel   (EXACT numerics: every step until the next binning)
 //       stages the tile from the cached layout (no cell-table look-ups, no reductions), runs the
 //       plain walk's fused pre-gate over the ~34 cached entries instead of ~160 candidates, and
@@ -221,7 +222,9 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     }
     const uint32_t t_self = work ? s - S.tslot[4] : 0xffffu;  // tile offset of the boid itself (row 4)
     if (total > 0) mbar_wait(&S.bar, 0);
-    uint16_t *const out = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + tid;  // entry k at out[k * BLOCK]
+    // entry k of this thread: [cta][k / 4][thread][k % 4] -- four consecutive entries are one 8-byte word
+    uint16_t *const out = nl.entries + ((size_t)blockIdx.x * (nl.vcap / 4) * NL_BLOCK + tid) * 4;
+    auto out_at = [&](uint32_t k) -> uint16_t & { return out[(size_t)(k >> 2) * (NL_BLOCK * 4) + (k & 3u)]; };
     uint16_t *const tmp = reinterpret_cast<uint16_t *>(smem_raw + sizeof(NlBuildSmem)) + tid;  // VIS_FIRST: [NB_TMP][BLOCK]
     const uint32_t vcap = nl.vcap;
     uint32_t w = 0;   // entries written to the list
@@ -266,7 +269,7 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
                         tmp[(size_t)wn * NL_BLOCK] = e;
                         ++wn;
                     } else {
-                        if (w < vcap) out[(size_t)w * NL_BLOCK] = e;
+                        if (w < vcap) out_at(w) = e;
                         ++w;
                     }
                 }
@@ -284,12 +287,17 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     }
     if (VIS_FIRST) {  // the entries not in view, behind the ones in view
         for (uint32_t k = 0; k < wn; ++k) {
-            if (w < vcap) out[(size_t)w * NL_BLOCK] = tmp[(size_t)k * NL_BLOCK];
+            if (w < vcap) out_at(w) = tmp[(size_t)k * NL_BLOCK];
             ++w;
         }
     }
     if (active) nl.count[s - io.first] = (uint16_t)min(w, vcap);
     if (__any_sync(0xffffffffu, w > vcap) && (tid & 31) == 0) nl_no_lists(nl, tab);
+    // Rows up to the warp's longest list (whole batches of four) are padded with a sentinel: the tile
+    // slot just past the staged candidates, which the walk fills with a position far outside any
+    // flock -- so the fast walk needs no per-entry "is this row mine" test.
+    const uint32_t wpad = min((__reduce_max_sync(0xffffffffu, min(w, vcap)) + 3u) & ~3u, vcap);
+    for (uint32_t k = min(w, vcap); k < wpad; ++k) out_at(k) = (uint16_t)nl.tile_cap;
 }
 
 struct NlWalkSmem {
@@ -327,10 +335,10 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
         vi4 = vel_s[s];
         n_c = __ldg(nl.count + (s - io.first));
     }
-    // this CTA's list block and the first batch of entries, in flight while the tile is staged
-    const uint16_t *const vlp = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + tid;
-    uint32_t e0 = __ldcs(vlp), e1 = __ldcs(vlp + NL_BLOCK), e2 = __ldcs(vlp + 2 * NL_BLOCK),
-             e3 = __ldcs(vlp + 3 * NL_BLOCK);
+    // this CTA's list block and its first two batches of entries, in flight while the tile is staged
+    // (four entries per 8-byte word; two batches in flight)
+    const uint2 *const vlp = reinterpret_cast<const uint2 *>(nl.entries) + (size_t)blockIdx.x * (nl.vcap / 4) * NL_BLOCK + tid;
+    uint2 q0 = __ldcs(vlp), q1 = __ldcs(vlp + NL_BLOCK);
     if (io.ctl) track_motion(io.ctl, active, pi4, vi4);
     Self self;
     self.p = self.v = self.vhat = v3zero();
@@ -371,13 +379,9 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
         uint32_t w = (uint32_t)cnt * NL_BLOCK;  // list cursor, in entries
 #pragma unroll 1
         for (uint32_t k = base; k < end; k += 4) {
-            const uint32_t c[4] = {e0, e1, e2, e3};
-            if (k + 4 < nmax) {  // the next batch: rows k + 4 .. k + 7 < vcap (vcap is a multiple of 4)
-                e0 = __ldcs(vlp + (size_t)(k + 4) * NL_BLOCK);
-                e1 = __ldcs(vlp + (size_t)(k + 5) * NL_BLOCK);
-                e2 = __ldcs(vlp + (size_t)(k + 6) * NL_BLOCK);
-                e3 = __ldcs(vlp + (size_t)(k + 7) * NL_BLOCK);
-            }
+            const uint32_t c[4] = {q0.x & 0xffffu, q0.x >> 16, q0.y & 0xffffu, q0.y >> 16};
+            q0 = q1;
+            if (k + 8 < nmax) q1 = __ldcs(vlp + (size_t)(k / 4 + 2) * NL_BLOCK);  // (rows < vcap: a multiple of 4)
             // The plain walk's pre-gate (fp_walk.cu), one candidate per lane-slot: fused squared
             // distance against m2_cut_hi, and the conservative FOV test KL m2 < q |q| < KH m2
             // (drops only pairs culled with a 1e-5 margin; NaN never drops).
@@ -425,8 +429,7 @@ struct FastPair {
     bool pass;    // contributes, decided outside the guard bands
     bool unsure;  // in range but degenerate or inside a guard band: the exact sequence decides
 };
-__device__ __forceinline__ FastPair fast_gate(const DevParams &P, const Self &self, float px, float py, float pz,
-                                              bool live) {
+__device__ __forceinline__ FastPair fast_gate(const DevParams &P, const Self &self, float px, float py, float pz) {
     FastPair f;
     f.dx = fsub(px, self.p.x);
     f.dy = fsub(py, self.p.y);
@@ -436,7 +439,7 @@ __device__ __forceinline__ FastPair fast_gate(const DevParams &P, const Self &se
     f.r = rsqrt_seed(f.m2);
     const float c = q * f.r;
     const float gc = (c - P.fz_a) * (c - P.fz_b);   // <= 0: culled (acosf(c) > max_sight_angle)
-    const bool in = live && !(f.m2 >= P.m2_cut);
+    const bool in = !(f.m2 >= P.m2_cut);  // (a padding entry is 1e18 away)
     // coincident positions (abs_diff_eq! guards, boid.rs:111,121), NaN, and cosines in the guard band
     const bool clear = fabsf(gc) > P.fz_gc_tol && f.m2 >= 1e-12f;
     f.unsure = in && !clear;
@@ -477,6 +480,7 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
         const uint32_t ub = tid < 9 ? __ldg(tab + tid) : 0u, ue = tid < 9 ? __ldg(tab + 9 + tid) : 0u;
         nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], NF_TILE, S.tv, io.vel_s);
     }
+    if (tid == 32) S.tx[NF_TILE] = S.ty[NF_TILE] = S.tz[NF_TILE] = 1e18f;  // the padding entries' "candidate"
 
     float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
     uint32_t n_c = 0;
@@ -485,9 +489,9 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
         vi4 = io.vel_s[s];
         n_c = __ldg(nl.count + (s - io.first));
     }
-    const uint16_t *const vlp = nl.entries + (size_t)blockIdx.x * nl.vcap * NL_BLOCK + tid;
-    uint32_t e0 = __ldcs(vlp), e1 = __ldcs(vlp + NL_BLOCK), e2 = __ldcs(vlp + 2 * NL_BLOCK),
-             e3 = __ldcs(vlp + 3 * NL_BLOCK);
+    // (four entries per 8-byte word; two batches in flight)
+    const uint2 *const vlp = reinterpret_cast<const uint2 *>(nl.entries) + (size_t)blockIdx.x * (nl.vcap / 4) * NL_BLOCK + tid;
+    uint2 q0 = __ldcs(vlp), q1 = __ldcs(vlp + NL_BLOCK);
     if (TAP == TAP_STEP && io.ctl) track_motion(io.ctl, active, pi4, vi4);
     Self self;
     self.p = self.v = self.vhat = v3zero();
@@ -497,7 +501,6 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
         const bool ghost = __float_as_uint(vi4.w) != 0u;
         work = !ghost && ((TAP != TAP_STEP) || !P.steering_overrides);
     }
-    if (!work) n_c = 0;
     if (no_lists) {  // a CTA without lists
         V3 acc = v3zero();
         if (work) acc = nl_walk_global(P, g, io, s, self);
@@ -511,21 +514,16 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
 #pragma unroll 1
     for (uint32_t k = 0; k < nmax; k += 4) {
-        const uint32_t c[4] = {e0, e1, e2, e3};
-        if (k + 4 < nmax) {
-            e0 = __ldcs(vlp + (size_t)(k + 4) * NL_BLOCK);
-            e1 = __ldcs(vlp + (size_t)(k + 5) * NL_BLOCK);
-            e2 = __ldcs(vlp + (size_t)(k + 6) * NL_BLOCK);
-            e3 = __ldcs(vlp + (size_t)(k + 7) * NL_BLOCK);
-        }
+        const uint32_t c[4] = {q0.x & 0xffffu, q0.x >> 16, q0.y & 0xffffu, q0.y >> 16};
+        q0 = q1;
+        if (k + 8 < nmax) q1 = __ldcs(vlp + (size_t)(k / 4 + 2) * NL_BLOCK);
         FastPair f[4];
         uint32_t t[4];
-        const uint32_t rem = n_c > k ? n_c - k : 0u;  // live entries of this batch
         bool any_unsure = false;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            t[u] = c[u] & 0xfffu;  // (entries past n_c hold offsets of earlier builds: inside the arrays, unused)
-            f[u] = fast_gate(P, self, S.tx[t[u]], S.ty[t[u]], S.tz[t[u]], (uint32_t)u < rem);
+            t[u] = c[u] & 0xfffu;  // (rows past this lane's list hold the build's padding entry)
+            f[u] = fast_gate(P, self, S.tx[t[u]], S.ty[t[u]], S.tz[t[u]]);
             any_unsure |= f[u].unsure;
         }
 #pragma unroll
@@ -536,7 +534,7 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
 #pragma unroll 1
             for (uint32_t u = 0; u < 4; ++u) {
                 const uint32_t tu = (u == 0 ? c[0] : u == 1 ? c[1] : u == 2 ? c[2] : c[3]) & 0xfffu;
-                const FastPair fu = fast_gate(P, self, S.tx[tu], S.ty[tu], S.tz[tu], u < rem);
+                const FastPair fu = fast_gate(P, self, S.tx[tu], S.ty[tu], S.tz[tu]);
                 if (!fu.unsure) continue;
                 const float4 vj = S.tv[tu];
                 V3 contrib;
@@ -550,6 +548,7 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
         }
     }
     if (!active) return;
+    if (!work) ax = ay = az = 0.0f;  // (steering overrides, ghost record: the lists were walked for nothing)
     walk_finish<TAP, true>(P, s, pi4, vi4, self, v3(ax, ay, az), 0u, 0ull, io, status, tap);
 }
 
@@ -557,7 +556,7 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
 
 size_t nl_entries_elems(uint32_t rows, uint32_t vcap) {
     const size_t ctas = ((size_t)rows + NL_BLOCK - 1) / NL_BLOCK;
-    return (ctas * vcap + 8) * NL_BLOCK;  // + slack rows: the walk's first batch is loaded unconditionally
+    return (ctas * vcap + 8) * NL_BLOCK;  // + slack rows: the walk's first two batches are loaded unconditionally
 }
 size_t nl_cta_tab_elems(uint32_t rows) {
     return (((size_t)rows + NL_BLOCK - 1) / NL_BLOCK) * NL_CTA_WORDS;
