@@ -322,8 +322,12 @@ class State {
     }
     std::vector<float> derivative() const { return flatten([](const T &t) { return t.derivative(); }); }
     std::vector<float> as_vector() const { return flatten([](const T &t) { return t.as_state(); }); }
-    // S + S' * h, combined on the device (state.rs:75-83)
+    // S + S' * h (state.rs:75-83).  A type that names the device kernel evaluating its derivative
+    // (`static int device_kind()` -> FP_STATEFUL_*, an ADDITION to the Stateful concept) is stepped
+    // entirely on the device -- one streaming pass, fp_state.cu; any other type keeps derivative()
+    // on the host and only the vector arithmetic runs on the device.
     State euler_step(float h) const {
+        if (const int kind = kind_of<T>(0)) return device_step(kind, h, false);
         const auto s = as_vector(), d = derivative();
         std::vector<float> out(s.size());
         fp_check(fp_state_euler_combine(device_, s.size(), s.data(), d.data(), h, out.data()));
@@ -331,6 +335,7 @@ class State {
     }
     // classic RK4 (state.rs:86-106): stages evaluated through T::derivative on the host
     State rk4_step(float h) const {
+        if (const int kind = kind_of<T>(0)) return device_step(kind, h, true);
         const auto s = as_vector();
         const auto k1 = derivative();
         const auto k2 = from_state_vector(axpy(s, k1, h * 0.5f), device_).derivative();
@@ -345,6 +350,21 @@ class State {
     const std::vector<T> &elements() const { return elements_; }
 
   private:
+    template <class U>
+    static auto kind_of(int) -> decltype(U::device_kind()) { return U::device_kind(); }
+    template <class U>
+    static int kind_of(...) { return 0; }
+    State device_step(int kind, float h, bool rk4) const {
+        const auto s = as_vector();
+        fp_state *st = nullptr;
+        fp_check(fp_state_create(&st, device_, kind, elements_.size(), s.data()));
+        const int rc = rk4 ? fp_state_rk4_step(st, h, 1) : fp_state_euler_step(st, h, 1);
+        std::vector<float> out(s.size());
+        const int rc2 = rc ? rc : fp_state_read(st, out.data());
+        fp_state_destroy(st);
+        fp_check(rc2);
+        return from_state_vector(out, device_);
+    }
     template <class F>
     std::vector<float> flatten(F f) const {
         std::vector<float> out;

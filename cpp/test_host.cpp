@@ -45,6 +45,30 @@ struct ExampleFn {
     std::vector<float> as_state() const { return {y, t, timestep}; }
 };
 
+// springy_mesh.rs:181-257 with the device kernel named: the whole step runs on the GPU
+struct SpringyPoint {
+    float mass;
+    Vector3 position, velocity, accumulated_force;
+    static size_t num_state_elements() { return 10; }
+    static int device_kind() { return FP_STATEFUL_SPRINGY_POINT; }
+    static SpringyPoint from_state_vector(std::vector<float> d) {
+        if (d.size() != num_state_elements()) throw Panic("State Vector incorrect size!");
+        return {d[0], {d[1], d[2], d[3]}, {d[4], d[5], d[6]}, {d[7], d[8], d[9]}};
+    }
+    std::vector<float> derivative() const {
+        return {0.0f, velocity[0], velocity[1], velocity[2], accumulated_force[0] / mass, accumulated_force[1] / mass,
+                accumulated_force[2] / mass, 0.0f, 0.0f, 0.0f};
+    }
+    std::vector<float> as_state() const {
+        return {mass, position[0], position[1], position[2], velocity[0], velocity[1], velocity[2],
+                accumulated_force[0], accumulated_force[1], accumulated_force[2]};
+    }
+};
+// the same type WITHOUT the addition: derivative() on the host, vector arithmetic on the device
+struct SpringyPointHost : SpringyPoint {
+    static SpringyPointHost from_state_vector(std::vector<float> d) { return {SpringyPoint::from_state_vector(std::move(d))}; }
+};
+
 static int host_only() {
     CHECK(flocking::Config().dt == 0.001f);
     CHECK(Duration::from_secs_f32(2.7f).secs == 2 && Duration::from_secs_f32(2.7f).nanos == 700000048u);
@@ -87,6 +111,20 @@ static int with_gpu() {
             CHECK(golden[k] + acceptable_error > v[0].y && golden[k] - acceptable_error < v[0].y);
             CHECK(v[0].t == ts[k] && v[0].timestep == 0.5f);
         }
+    }
+    {   // State<Point> of the springy mesh: device-resident kernel == host derivative + device combine
+        std::vector<SpringyPoint> dev;
+        std::vector<SpringyPointHost> host;
+        for (int i = 0; i < 1000; ++i) {
+            const float f = (float)i;
+            SpringyPoint p{1.0f + 0.01f * f, {f, 2.0f * f, -f}, {0.5f, -0.25f * f, 0.125f}, {0.3f * f, -9.8f, 0.7f}};
+            dev.push_back(p);
+            host.push_back({p});
+        }
+        auto a = state::State<SpringyPoint>(dev).rk4_step(0.01f).euler_step(0.02f).as_vector();
+        auto b = state::State<SpringyPointHost>(host).rk4_step(0.01f).euler_step(0.02f).as_vector();
+        CHECK(a.size() == 10000 && std::memcmp(a.data(), b.data(), a.size() * 4) == 0);
+        CHECK(a[4] != 0.5f);
     }
     {   // the demo's sim 1 (demos/flocking.rs:105-121) stepped headless two ways: must agree bit for bit
         std::vector<float> st;

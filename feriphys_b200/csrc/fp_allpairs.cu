@@ -300,13 +300,13 @@ allpairs2_kernel(const DevParams P, const float4 *__restrict__ pos_all,
 constexpr int APF_TJ = 256;  // candidates per tile
 
 struct ApfSmem {
-    alignas(16) float xc[APF_TJ], yc[APF_TJ], zc[APF_TJ], w[APF_TJ];  // centred position, |.|^2
+    alignas(16) float xc[APF_TJ], yc[APF_TJ], zc[APF_TJ], w[APF_TJ];  // -2 x centred position, |centred|^2
     float4 tp[APF_TJ], tv[APF_TJ];                                    // the records themselves
 };
 
 struct ApfBoid {
     Self self;
-    float2 ax2, ay2, az2;  // -2 (p - centre), both halves
+    float2 ax2, ay2, az2;  // p - centre, both halves
     float thr;             // cut + margin - |p - centre|^2
     float ax, ay, az;      // partial acceleration
 };
@@ -394,9 +394,9 @@ allpairs_fast_kernel(const DevParams P, const float4 *__restrict__ pos_all, cons
         vi4[k] = __ldg(vel_all + i);
         b[k].self = make_self(v3(pi4[k].x, pi4[k].y, pi4[k].z), v3(vi4[k].x, vi4[k].y, vi4[k].z));
         const float px = pi4[k].x - cx, py = pi4[k].y - cy, pz = pi4[k].z - cz;
-        b[k].ax2 = make_float2(-2.0f * px, -2.0f * px);
-        b[k].ay2 = make_float2(-2.0f * py, -2.0f * py);
-        b[k].az2 = make_float2(-2.0f * pz, -2.0f * pz);
+        b[k].ax2 = make_float2(px, px);
+        b[k].ay2 = make_float2(py, py);
+        b[k].az2 = make_float2(pz, pz);
         b[k].thr = (P.m2_cut + margin) - fmaf(pz, pz, fmaf(py, py, px * px));
         b[k].ax = b[k].ay = b[k].az = 0.0f;
     }
@@ -414,7 +414,7 @@ allpairs_fast_kernel(const DevParams P, const float4 *__restrict__ pos_all, cons
                     vj = __ldg(vel_all + jl);
                 }
                 const float x = pj.x - cx, y = pj.y - cy, z = pj.z - cz;
-                S.xc[t] = x; S.yc[t] = y; S.zc[t] = z;
+                S.xc[t] = -2.0f * x; S.yc[t] = -2.0f * y; S.zc[t] = -2.0f * z;  // (the -2 of -2 p_i . p_j, exact)
                 S.w[t] = fmaf(z, z, fmaf(y, y, x * x));
                 S.tp[t] = pj;
                 S.tv[t] = vj;
@@ -422,36 +422,47 @@ allpairs_fast_kernel(const DevParams P, const float4 *__restrict__ pos_all, cons
             __syncthreads();
             const uint32_t cnt = min((uint32_t)APF_TJ, n_all - j0);
             uint32_t tried = 0, hits = 0;
-            for (uint32_t q = slice; 4u * q < cnt; q += JS) {
-                bool hit = dense;
-                if (!dense) {
-                    const float4 X = *reinterpret_cast<const float4 *>(&S.xc[4 * q]);
-                    const float4 Y = *reinterpret_cast<const float4 *>(&S.yc[4 * q]);
-                    const float4 Z = *reinterpret_cast<const float4 *>(&S.zc[4 * q]);
-                    const float4 W = *reinterpret_cast<const float4 *>(&S.w[4 * q]);
-                    const float2 X01 = make_float2(X.x, X.y), X23 = make_float2(X.z, X.w);
-                    const float2 Y01 = make_float2(Y.x, Y.y), Y23 = make_float2(Y.z, Y.w);
-                    const float2 Z01 = make_float2(Z.x, Z.y), Z23 = make_float2(Z.z, Z.w);
-                    const float2 W01 = make_float2(W.x, W.y), W23 = make_float2(W.z, W.w);
+            // one compare per boid and batch of four candidates.  (fminf drops a NaN operand: a record
+            // with a non-finite position can go unseen here -- FAST numerics are defined on finite states.)
+            auto pregate = [&](uint32_t q) -> bool {
+                const float4 X = *reinterpret_cast<const float4 *>(&S.xc[4 * q]);
+                const float4 Y = *reinterpret_cast<const float4 *>(&S.yc[4 * q]);
+                const float4 Z = *reinterpret_cast<const float4 *>(&S.zc[4 * q]);
+                const float4 W = *reinterpret_cast<const float4 *>(&S.w[4 * q]);
+                const float2 X01 = make_float2(X.x, X.y), X23 = make_float2(X.z, X.w);
+                const float2 Y01 = make_float2(Y.x, Y.y), Y23 = make_float2(Y.z, Y.w);
+                const float2 Z01 = make_float2(Z.x, Z.y), Z23 = make_float2(Z.z, Z.w);
+                const float2 W01 = make_float2(W.x, W.y), W23 = make_float2(W.z, W.w);
+                bool hit = false;
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const float2 t01 = __ffma2_rn(b[k].ax2, X01, __ffma2_rn(b[k].ay2, Y01, __ffma2_rn(b[k].az2, Z01, W01)));
-                        const float2 t23 = __ffma2_rn(b[k].ax2, X23, __ffma2_rn(b[k].ay2, Y23, __ffma2_rn(b[k].az2, Z23, W23)));
-                        // one compare per boid and batch.  (fminf drops a NaN operand: a record with a
-                        // non-finite position can go unseen here -- FAST numerics are defined on finite states.)
-                        hit |= !(fminf(fminf(t01.x, t01.y), fminf(t23.x, t23.y)) >= b[k].thr);
-                    }
-                    ++tried;
-                    hits += hit ? 1u : 0u;
+                for (int k = 0; k < 2; ++k) {
+                    const float2 t01 = __ffma2_rn(b[k].ax2, X01, __ffma2_rn(b[k].ay2, Y01, __ffma2_rn(b[k].az2, Z01, W01)));
+                    const float2 t23 = __ffma2_rn(b[k].ax2, X23, __ffma2_rn(b[k].ay2, Y23, __ffma2_rn(b[k].az2, Z23, W23)));
+                    hit |= !(fminf(fminf(t01.x, t01.y), fminf(t23.x, t23.y)) >= b[k].thr);
                 }
-                if (hit) {  // someone may be in range: the whole batch takes the exact distance test
+                return hit;
+            };
+            auto pairs = [&](uint32_t q) {  // someone may be in range: the whole batch takes the exact distance test
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t t = 4 * q + u;
-                        const float4 pj = S.tp[t];
-                        apf_pair<FOV>(P, b[0], pj, &S.tv[t], t < cnt);
-                        apf_pair<FOV>(P, b[1], pj, &S.tv[t], t < cnt);
-                    }
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t t = 4 * q + u;
+                    const float4 pj = S.tp[t];
+                    apf_pair<FOV>(P, b[0], pj, &S.tv[t], t < cnt);
+                    apf_pair<FOV>(P, b[1], pj, &S.tv[t], t < cnt);
+                }
+            };
+            if (dense) {
+                for (uint32_t q = slice; 4u * q < cnt; q += JS) pairs(q);
+            } else {
+                // two batches per trip: their pre-gates are independent chains
+                for (uint32_t q = slice; 4u * q < cnt; q += 2 * JS) {
+                    const uint32_t q2 = q + JS;
+                    const bool two = 4u * q2 < cnt;
+                    const bool h1 = pregate(q), h2 = two && pregate(q2);
+                    tried += two ? 2u : 1u;
+                    hits += (h1 ? 1u : 0u) + (h2 ? 1u : 0u);
+                    if (h1) pairs(q);
+                    if (h2) pairs(q2);
                 }
             }
             // a dense flock (C2: half of all pairs are in range) gains nothing from the pre-gate: once
