@@ -540,6 +540,13 @@ bool nl_enabled() {
     }();
     return on;
 }
+bool nl_prefetch_enabled() {  // FP_NL_PREFETCH=0: no L2 warming for the CTA that comes next
+    static const bool on = [] {
+        const char *e = getenv("FP_NL_PREFETCH");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 bool nl_trace() {
     static const bool on = getenv("FP_NL_TRACE") != nullptr;
     return on;
@@ -601,6 +608,8 @@ NlIO nl_io(const fp_flock *f, double skins = 1.0) {
     nl.flag = f->nl_flag;
     nl.vcap = NL_VCAP;
     nl.tile_cap = nl_tile_cap(f->P.numerics_fast != 0);
+    nl.tile_cap_b = nl_tile_cap_b(f->P.numerics_fast != 0);
+    nl.ahead = nl_prefetch_enabled() ? nl_walk_resident_ctas(f->P.numerics_fast != 0) : 0u;
     // every pair within reach while the binning stands was within reach + skin when it was made
     // (skins = 2: within reach + 2 skin at any other moment of the binning's life)
     const double R = (double)reach_of(f->cfg) + skins * (double)f->grid.skin;

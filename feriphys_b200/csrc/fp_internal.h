@@ -170,6 +170,8 @@ struct NlIO {
     unsigned *flag;      // [0]: CTAs the last build left without lists (tile or list overflow)
     uint32_t vcap;       // list capacity, a multiple of 4
     uint32_t tile_cap;   // staged candidates the walk that will use the lists can hold per CTA
+    uint32_t tile_cap_b; // ... in its positions-only form (fast walk; 0: there is no such form)
+    uint32_t ahead;      // walk: CTAs resident on the device at once -- CTA b warms L2 for CTA b + ahead (0: off)
     float m2_wide;       // build cut: (reach + skin)^2 (1 + 1e-5)
     int vis_first;       // order each list with the entries predicted to be in view first (fast walk)
     float vis_c;         // ... in view <=> cosine of the sight angle > vis_c
@@ -177,6 +179,8 @@ struct NlIO {
 size_t nl_entries_elems(uint32_t rows, uint32_t vcap);
 size_t nl_cta_tab_elems(uint32_t rows);
 uint32_t nl_tile_cap(bool fast);
+uint32_t nl_tile_cap_b(bool fast);
+uint32_t nl_walk_resident_ctas(bool fast);
 // after a binning, before the first walk that uses the lists
 int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl);
 // a step (TAP_STEP) -- or, under FAST numerics, the acceleration tap -- on the standing lists.

@@ -46,12 +46,106 @@ namespace {
 constexpr int NL_BLOCK = 128;   // threads (= boids) per CTA, as the plain walk
 constexpr int NL_TILE = 1904;   // staged candidates per CTA (build and exact walk), as the plain walk
 constexpr int NL_CAP = 48;      // survivor list of the exact walk (shared memory): six CTAs per SM
-constexpr int NF_TILE = 1568;   // staged candidates per CTA of the fast walk (positions + velocities)
+constexpr int NF_TILE = 1568;   // staged candidates per CTA of the fast walk, form A (positions + velocities)
+constexpr int NF_TILE_B = 3648; // ... form B (positions only)
 constexpr int NL_CTA_WORDS = 20;  // cached tile layout per CTA: ub[9], ue[9], [18] = no lists, 1 spare
 
 // this CTA gets no lists: it walks from global memory every step (counted once per CTA)
 __device__ __forceinline__ void nl_no_lists(const NlIO &nl, uint32_t *tab) {
     if (atomicExch(tab + 18, 1u) == 0u) atomicAdd(nl.flag, 1u);
+}
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t *p) {  // (volatile: issued where it stands)
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// What every list walk starts with.  All loads of the prologue are issued before anything waits on
+// one of them -- the step's validity, the CTA's layout record, the boid, its list length, its first
+// two words of entries -- and, into L2 only, the same items of the CTA that will take this one's
+// place `nl.ahead` blocks on: its prologue then waits for L2, not for HBM (the start-up chain
+// layout -> TMA -> tile was a third of the kernel's stall samples, profiles/r2_c4_nl_fast_v3_*).
+struct NlPrologue {
+    uint32_t stale, no_lists, ub, ue, n_c;
+    float4 pi4, vi4;
+    const uint2 *vlp;
+    uint2 q0, q1;
+    bool pf;            // this CTA warms L2 for a successor
+    uint32_t ub2, ue2;  // the successor's intervals (threads 32 .. 40)
+};
+template <bool STEP, bool EARLY2>  // EARLY2: the successor's intervals are loaded here (two registers), else later
+__device__ __forceinline__ NlPrologue nl_prologue(const WalkIO &io, const NlIO &nl, uint32_t tid, uint32_t s,
+                                                  bool active) {
+    NlPrologue p;
+    const uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
+    p.stale = (STEP && io.ctl) ? ld_relaxed_u32(&io.ctl->stale) : 0u;
+    p.no_lists = ld_nc_u32(tab + 18);
+    p.ub = p.ue = 0;
+    if (tid < 9) {
+        p.ub = ld_nc_u32(tab + tid);
+        p.ue = ld_nc_u32(tab + 9 + tid);
+    }
+    p.pi4 = p.vi4 = make_float4(0, 0, 0, 0);
+    p.n_c = 0;
+    if (active) {
+        p.pi4 = io.pos_s[s];
+        p.vi4 = io.vel_s[s];
+        p.n_c = __ldg(nl.count + (s - io.first));
+    }
+    // this CTA's list block: four entries per 8-byte word, [word][thread]
+    p.vlp = reinterpret_cast<const uint2 *>(nl.entries) + (size_t)blockIdx.x * (nl.vcap / 4) * NL_BLOCK + tid;
+    p.q0 = __ldcs(p.vlp);
+    p.q1 = __ldcs(p.vlp + NL_BLOCK);
+    p.pf = nl.ahead && blockIdx.x + nl.ahead < gridDim.x;
+    p.ub2 = p.ue2 = 0;
+    if (p.pf) {
+        const uint32_t s2 = s + nl.ahead * NL_BLOCK;
+        if (s2 < io.last) {
+            prefetch_l2(io.pos_s + s2);
+            prefetch_l2(io.vel_s + s2);
+        }
+        prefetch_l2(p.vlp + (size_t)nl.ahead * (nl.vcap / 4) * NL_BLOCK);
+        prefetch_l2(p.vlp + (size_t)nl.ahead * (nl.vcap / 4) * NL_BLOCK + NL_BLOCK);
+        if (EARLY2) {
+            if (tid >= 32 && tid < 41) {
+                p.ub2 = ld_nc_u32(tab + (size_t)nl.ahead * NL_CTA_WORDS + (tid - 32));
+                p.ue2 = ld_nc_u32(tab + (size_t)nl.ahead * NL_CTA_WORDS + 9 + (tid - 32));
+            }
+        } else if (tid == 32) {
+            prefetch_l2(tab + (size_t)nl.ahead * NL_CTA_WORDS);
+        }
+    }
+    return p;
+}
+// the successor's tile, into L2 (threads 32 .. 40, once this CTA's own tile has landed)
+template <bool EARLY2>
+__device__ __forceinline__ void nl_warm_successor(const NlPrologue &p, const WalkIO &io, const NlIO &nl, uint32_t tid,
+                                                  bool vel) {
+    if (p.pf && tid >= 32 && tid < 41) {
+        uint32_t ub2 = p.ub2, ue2 = p.ue2;
+        if (!EARLY2) {
+            const uint32_t *const tab2 = nl.cta_tab + ((size_t)blockIdx.x + nl.ahead) * NL_CTA_WORDS;
+            ub2 = ld_nc_u32(tab2 + (tid - 32));
+            ue2 = ld_nc_u32(tab2 + 9 + (tid - 32));
+        }
+        if (ue2 > ub2) {
+            const uint32_t bytes = (ue2 - ub2) * 4u;
+            bulk_prefetch_l2(io.soa_in[0] + ub2, bytes);
+            bulk_prefetch_l2(io.soa_in[1] + ub2, bytes);
+            bulk_prefetch_l2(io.soa_in[2] + ub2, bytes);
+            if (vel) bulk_prefetch_l2(io.vel_s + ub2, bytes * 4u);
+        }
+    }
 }
 
 // Lays the nine CTA-wide intervals (ub, ue: multiples of 4, empty = 0, 0) out in the tile and
@@ -116,8 +210,9 @@ __device__ __forceinline__ V3 nl_walk_global(const DevParams &P, const GridDesc 
     return acc;
 }
 
+template <int TILE>
 struct NlBuildSmem {
-    alignas(16) float tx[NL_TILE + 8], ty[NL_TILE + 8], tz[NL_TILE + 8];
+    alignas(16) float tx[TILE + 8], ty[TILE + 8], tz[TILE + 8];
     uint32_t rng[9][NL_BLOCK];  // per-thread (tile start | len << 16) per row
     uint32_t ub[9], ue[9];
     uint32_t toff[10], tslot[9];
@@ -130,13 +225,16 @@ constexpr int NB_TMP = 64;  // VIS_FIRST: entries held back in shared memory (th
 // sight angle against nl.vis_c, from the velocities of this moment -- are written first, the others
 // after them (each class in ascending slot order).  Any order is a correct list; this one makes the
 // lanes of a warp agree on whether row k contributes.
-template <bool VIS_FIRST>
+template <bool VIS_FIRST, int TILE>
 __global__ void __launch_bounds__(NL_BLOCK)
 nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     // (No look at ctl->stale: the lists describe the binning, which stands whether or not the
     // step they are built in turns out void.)
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    NlBuildSmem &S = *reinterpret_cast<NlBuildSmem *>(smem_raw);
+    using Smem = NlBuildSmem<TILE>;
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    // the walk that will use the lists holds nl.tile_cap candidates, or (fast walk, form B) nl.tile_cap_b
+    const uint32_t cap_max = nl.tile_cap_b ? nl.tile_cap_b : nl.tile_cap;
     const uint32_t tid = threadIdx.x;
     const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
     const bool active = s < io.last;
@@ -206,11 +304,11 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
             tab[tid] = ub;       // the layout every walk launch of this binning re-uses
             tab[9 + tid] = ue;
         }
-        nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], nl.tile_cap);
+        nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], cap_max);
     }
     __syncthreads();
     const uint32_t total = S.toff[9];
-    if (total > nl.tile_cap) {  // dense cluster: the tile does not fit -- no lists for this CTA
+    if (total > cap_max) {  // dense cluster: the tile does not fit -- no lists for this CTA
         if (tid == 0) nl_no_lists(nl, tab);
         return;
     }
@@ -225,7 +323,7 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     // entry k of this thread: [cta][k / 4][thread][k % 4] -- four consecutive entries are one 8-byte word
     uint16_t *const out = nl.entries + ((size_t)blockIdx.x * (nl.vcap / 4) * NL_BLOCK + tid) * 4;
     auto out_at = [&](uint32_t k) -> uint16_t & { return out[(size_t)(k >> 2) * (NL_BLOCK * 4) + (k & 3u)]; };
-    uint16_t *const tmp = reinterpret_cast<uint16_t *>(smem_raw + sizeof(NlBuildSmem)) + tid;  // VIS_FIRST: [NB_TMP][BLOCK]
+    uint16_t *const tmp = reinterpret_cast<uint16_t *>(smem_raw + sizeof(Smem)) + tid;  // VIS_FIRST: [NB_TMP][BLOCK]
     const uint32_t vcap = nl.vcap;
     uint32_t w = 0;   // entries written to the list
     uint32_t wn = 0;  // VIS_FIRST: entries held back (not in view)
@@ -297,7 +395,8 @@ nl_build_kernel(const GridDesc g, const WalkIO io, const NlIO nl) {
     // slot just past the staged candidates, which the walk fills with a position far outside any
     // flock -- so the fast walk needs no per-entry "is this row mine" test.
     const uint32_t wpad = min((__reduce_max_sync(0xffffffffu, min(w, vcap)) + 3u) & ~3u, vcap);
-    for (uint32_t k = min(w, vcap); k < wpad; ++k) out_at(k) = (uint16_t)nl.tile_cap;
+    const uint32_t pad = total > nl.tile_cap ? nl.tile_cap_b : nl.tile_cap;  // the slot just past the walk's tile
+    for (uint32_t k = min(w, vcap); k < wpad; ++k) out_at(k) = (uint16_t)pad;
 }
 
 struct NlWalkSmem {
@@ -312,33 +411,24 @@ struct NlWalkSmem {
 // CTAs per SM: C4 3.34 against 3.55 ms, profiles/r2_bench_*).
 __global__ void __launch_bounds__(NL_BLOCK, 6)
 nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO nl, unsigned *__restrict__ status) {
-    if (io.ctl && io.ctl->stale) return;  // lazy re-binning: this step is void
     const float4 *__restrict__ vel_s = io.vel_s;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     NlWalkSmem &S = *reinterpret_cast<NlWalkSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
     const bool active = s < io.last;
-    const uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
-    const bool no_lists = __ldg(tab + 18) != 0u;
-    if (tid < 32 && !no_lists) {  // warp 0 gets the tile moving before anything else
+    const NlPrologue pro = nl_prologue<true, false>(io, nl, tid, s, active);
+    if (pro.stale) return;  // lazy re-binning: this step is void (nothing staged, nothing written yet)
+    const bool no_lists = pro.no_lists != 0u;
+    if (tid < 32 && !no_lists) {  // warp 0 gets the tile moving
         if (tid == 0) mbar_init(&S.bar, 1);
         __syncwarp();
-        const uint32_t ub = tid < 9 ? __ldg(tab + tid) : 0u, ue = tid < 9 ? __ldg(tab + 9 + tid) : 0u;
-        nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], NL_TILE);
+        nl_stage(S, tid, pro.ub, pro.ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], NL_TILE);
     }
-
-    float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
-    uint32_t n_c = 0;  // cached candidates of this boid
-    if (active) {
-        pi4 = io.pos_s[s];
-        vi4 = vel_s[s];
-        n_c = __ldg(nl.count + (s - io.first));
-    }
-    // this CTA's list block and its first two batches of entries, in flight while the tile is staged
-    // (four entries per 8-byte word; two batches in flight)
-    const uint2 *const vlp = reinterpret_cast<const uint2 *>(nl.entries) + (size_t)blockIdx.x * (nl.vcap / 4) * NL_BLOCK + tid;
-    uint2 q0 = __ldcs(vlp), q1 = __ldcs(vlp + NL_BLOCK);
+    const float4 pi4 = pro.pi4, vi4 = pro.vi4;
+    uint32_t n_c = pro.n_c;  // cached candidates of this boid
+    const uint2 *const vlp = pro.vlp;
+    uint2 q0 = pro.q0, q1 = pro.q1;  // (two batches of entries in flight)
     if (io.ctl) track_motion(io.ctl, active, pi4, vi4);
     Self self;
     self.p = self.v = self.vhat = v3zero();
@@ -360,6 +450,7 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     const uint32_t t_self = work ? s - S.tslot[4] : 0xffffu;
     const uint32_t nmax = __reduce_max_sync(0xffffffffu, n_c);
     if (S.toff[9] > 0) mbar_wait(&S.bar, 0);  // (a layout with lists always fits the tile)
+    nl_warm_successor<false>(pro, io, nl, tid, false);
 
     uint16_t *const lst = &S.list[0][tid];  // entry k at lst[k * BLOCK]
     int cnt = 0;
@@ -412,86 +503,217 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
 }
 
 // ---- FAST numerics ----------------------------------------------------------------------------
-struct NlFastSmem {
-    alignas(16) float tx[NF_TILE + 8], ty[NF_TILE + 8], tz[NF_TILE + 8];
-    alignas(16) float4 tv[NF_TILE];  // velocities of the staged candidates (.w: record flag, unused)
+// Shared memory of the fast walk, 44 KB either way (five CTAs per SM):
+//   form A (the nine intervals hold <= NF_TILE candidates): x, y, z AND velocities staged by TMA;
+//   form B (<= NF_TILE_B): positions only, the velocity of a contributing pair comes from global
+//          memory (L1 / L2: the CTA's boids share their candidates).  A CTA whose boids straddle
+//          two cell columns has a union of intervals ~15 % above the average; with form A alone
+//          1.4 % of C4's CTAs overflowed the tile and walked their 27 cells from global memory with
+//          the exact pair function -- 9 % of the kernel's time (profiles/r2_c4_nl_fast_v3_*).
+constexpr int NF_STRIDE_A = NF_TILE + 8, NF_STRIDE_B = NF_TILE_B + 8;  // floats per coordinate array
+constexpr int NF_SMEM_FLOATS = 3 * NF_STRIDE_A + 4 * NF_TILE;          // form A: 44 000 B
+static_assert(3 * NF_STRIDE_B <= NF_SMEM_FLOATS, "form B must fit the same buffer");
+struct NlFastTail {  // behind the tile
     uint32_t toff[10], tslot[9];
     alignas(8) uint64_t bar;
 };
 
-// One entry of a boid's cached list under FAST numerics.  The squared distance is the reference's
-// own (separately rounded, boid.rs:94-96 through cgmath's dot), so "in range" and "weight 1" are its
-// decisions.  The cosine of the sight angle is fused and uses MUFU.RSQ: within ~1e-6 of the
-// reference's (boid.rs:102-105); the decision is taken on it when it is further than the guard band
-// from both ends of the culled interval [-1, cstar], else `unsure` sends the pair down the exact path.
-struct FastPair {
-    float dx, dy, dz, m2, r;
-    bool pass;    // contributes, decided outside the guard bands
-    bool unsure;  // in range but degenerate or inside a guard band: the exact sequence decides
+
+// Two entries of a boid's cached list under FAST numerics, in the two halves of packed FP32
+// registers (FADD2 / FMUL2 / FFMA2: one issue slot for both).  The squared distance is the
+// reference's own (separately rounded, boid.rs:94-96 through cgmath's dot), so "in range" and
+// "weight 1" are its decisions.  The cosine of the sight angle is fused and uses MUFU.RSQ: within
+// ~1e-6 of the reference's (boid.rs:102-105); the decision is taken on it when it is further than
+// the guard band from both ends of the culled interval [-1, cstar], else `unsure` sends the pair
+// down the exact path.
+struct FastSelf {
+    float px, py, pz;  // position
+    float hx, hy, hz;  // direction of flight
+    float vx, vy, vz;  // velocity
 };
-__device__ __forceinline__ FastPair fast_gate(const DevParams &P, const Self &self, float px, float py, float pz) {
-    FastPair f;
-    f.dx = fsub(px, self.p.x);
-    f.dy = fsub(py, self.p.y);
-    f.dz = fsub(pz, self.p.z);
-    f.m2 = fadd(fadd(fmul(f.dx, f.dx), fmul(f.dy, f.dy)), fmul(f.dz, f.dz));
-    const float q = fmaf(self.vhat.z, f.dz, fmaf(self.vhat.y, f.dy, self.vhat.x * f.dx));
-    f.r = rsqrt_seed(f.m2);
-    const float c = q * f.r;
-    const float gc = (c - P.fz_a) * (c - P.fz_b);   // <= 0: culled (acosf(c) > max_sight_angle)
-    const bool in = !(f.m2 >= P.m2_cut);  // (a padding entry is 1e18 away)
-    // coincident positions (abs_diff_eq! guards, boid.rs:111,121), NaN, and cosines in the guard band
-    const bool clear = fabsf(gc) > P.fz_gc_tol && f.m2 >= 1e-12f;
-    f.unsure = in && !clear;
-    f.pass = in && clear && gc > 0.0f;
+struct FastPair2 {
+    float2 dx, dy, dz, m2, r, gc;
+};
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+__device__ __forceinline__ FastPair2 fast_gate2(const DevParams &P, const FastSelf &F, float2 px, float2 py,
+                                                float2 pz) {
+    FastPair2 f;
+    f.dx = __fadd2_rn(px, f2s(-F.px));
+    f.dy = __fadd2_rn(py, f2s(-F.py));
+    f.dz = __fadd2_rn(pz, f2s(-F.pz));
+    // (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 -- the explicit rounding modifiers do
+    //  not stop it as they do for scalars -- but never a packed product with a scalar add: the sums
+    //  are scalar, each product and each sum separately rounded as in the reference)
+    const float2 xx = __fmul2_rn(f.dx, f.dx), yy = __fmul2_rn(f.dy, f.dy), zz = __fmul2_rn(f.dz, f.dz);
+    f.m2 = f2(fadd(fadd(xx.x, yy.x), zz.x), fadd(fadd(xx.y, yy.y), zz.y));
+    const float2 q = __ffma2_rn(f2s(F.hz), f.dz, __ffma2_rn(f2s(F.hy), f.dy, __fmul2_rn(f2s(F.hx), f.dx)));
+    f.r = f2(rsqrt_seed(f.m2.x), rsqrt_seed(f.m2.y));
+    const float2 c = __fmul2_rn(q, f.r);
+    // <= 0: culled (acosf(c) > max_sight_angle); NaN for coincident positions (0 x inf)
+    f.gc = __fmul2_rn(__fadd2_rn(c, f2s(-P.fz_a)), __fadd2_rn(c, f2s(-P.fz_b)));
     return f;
 }
-// contribution of a pair that passed, accumulated with FMAs: w_d ((av + ce) + vm)  (boid.rs:162-165)
-__device__ __forceinline__ void fast_force(const DevParams &P, const Self &self, const FastPair &f, float4 vj,
-                                           float &ax, float &ay, float &az) {
+// contributions of the two pairs (those that passed), accumulated with FMAs into packed partial sums:
+// w_d ((av + ce) + vm)  (boid.rs:162-165)
+__device__ __forceinline__ void fast_force2(const DevParams &P, const FastSelf &F, const FastPair2 &f, bool pass_a,
+                                            bool pass_b, float4 va, float4 vb, float2 &ax, float2 &ay, float2 &az) {
     // dist: the seed refined to the correctly rounded square root (it enters the ramp by difference)
-    const float g0 = f.m2 * f.r, h = 0.5f * f.r;
-    const float mag = fmaf(fmaf(-g0, g0, f.m2), h, g0);
-    const float coef = fmaf(P.f_c, mag, P.neg_f_a * (f.r * f.r)) * f.r;  // ((-f_a / d^2) + f_c d) / d, on d
-    const float w = f.m2 <= P.m2_one ? 1.0f : (mag - P.thr) * P.fz_rinv_fall;  // boid.rs:152-161 (F7)
-    const float dvx = vj.x - self.v.x, dvy = vj.y - self.v.y, dvz = vj.z - self.v.z;
-    const bool vsm = fmaxf(fmaxf(fabsf(dvx), fabsf(dvy)), fabsf(dvz)) <= FP_F32_EPSILON;  // boid.rs:132
-    const float cw = coef * w, fw = vsm ? 0.0f : P.f_v * w;
-    ax = fmaf(cw, f.dx, fmaf(fw, dvx, ax));
-    ay = fmaf(cw, f.dy, fmaf(fw, dvy, ay));
-    az = fmaf(cw, f.dz, fmaf(fw, dvz, az));
+    const float2 g0 = __fmul2_rn(f.m2, f.r), h = __fmul2_rn(f.r, f2s(0.5f));
+    const float2 mag = __ffma2_rn(__ffma2_rn(f2(-g0.x, -g0.y), g0, f.m2), h, g0);
+    // ((-f_a / d^2) + f_c d) / d, on d
+    const float2 coef = __fmul2_rn(__ffma2_rn(f2s(P.f_c), mag, __fmul2_rn(f2s(P.neg_f_a), __fmul2_rn(f.r, f.r))), f.r);
+    const float2 ramp = __fmul2_rn(__fadd2_rn(mag, f2s(-P.thr)), f2s(P.fz_rinv_fall));  // boid.rs:152-161 (F7)
+    const float2 w = f2(f.m2.x <= P.m2_one ? 1.0f : ramp.x, f.m2.y <= P.m2_one ? 1.0f : ramp.y);
+    const float2 dvx = f2(va.x - F.vx, vb.x - F.vx), dvy = f2(va.y - F.vy, vb.y - F.vy),
+                 dvz = f2(va.z - F.vz, vb.z - F.vz);
+    // velocity matching unless the velocities agree to EPSILON (boid.rs:132)
+    const bool ma = pass_a && !(fmaxf(fmaxf(fabsf(dvx.x), fabsf(dvy.x)), fabsf(dvz.x)) <= FP_F32_EPSILON);
+    const bool mb = pass_b && !(fmaxf(fmaxf(fabsf(dvx.y), fabsf(dvy.y)), fabsf(dvz.y)) <= FP_F32_EPSILON);
+    float2 cw = __fmul2_rn(coef, w), fw = __fmul2_rn(f2s(P.f_v), w);
+    // (a pair that did not pass may hold inf / NaN in coef: selected away, never multiplied away)
+    cw = f2(pass_a ? cw.x : 0.0f, pass_b ? cw.y : 0.0f);
+    fw = f2(ma ? fw.x : 0.0f, mb ? fw.y : 0.0f);
+    ax = __ffma2_rn(cw, f.dx, __ffma2_rn(fw, dvx, ax));
+    ay = __ffma2_rn(cw, f.dy, __ffma2_rn(fw, dvy, ay));
+    az = __ffma2_rn(cw, f.dz, __ffma2_rn(fw, dvz, az));
+}
+
+// The pass over a boid's cached entries.  FORM_B: velocities from global memory.
+// Decisions per entry (finite states): in range <=> m2 < m2_cut, the reference's own squared distance;
+// contributes <=> gc > tol (visible, outside the guard band); `unsure` <=> |gc| <= tol or NaN (guard
+// band; coincident positions).  A batch with a pair closer than 1e-6 (the abs_diff_eq! guards of
+// boid.rs:111,121 may apply) is evaluated by the exact sequence altogether.
+template <bool FORM_B>
+__device__ __forceinline__ void fast_entries(const DevParams &P, const Self &self, const uint32_t *tslot,
+                                             const float4 *__restrict__ vel_s, const uint2 *__restrict__ vlp,
+                                             uint32_t nmax, uint2 q0, uint2 q1, float &ax_out, float &ay_out,
+                                             float &az_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int STRIDE = FORM_B ? NF_STRIDE_B : NF_STRIDE_A;
+    const float *const tx = reinterpret_cast<const float *>(smem_raw);
+    const float *const ty = tx + STRIDE, *const tz = tx + 2 * STRIDE;
+    const float4 *const tv = reinterpret_cast<const float4 *>(tx + 3 * NF_STRIDE_A);  // (form A)
+    const FastSelf F{self.p.x, self.p.y, self.p.z, self.vhat.x, self.vhat.y, self.vhat.z, self.v.x, self.v.y, self.v.z};
+    // velocity of an entry that contributes (form B: a padding entry has no slot to read)
+    auto vel_of = [&](uint32_t c, bool wanted) -> float4 {
+        const uint32_t t = c & 0xfffu;
+        if (!FORM_B) return tv[t];
+        return wanted ? __ldg(vel_s + (tslot[c >> 12] + t)) : make_float4(0, 0, 0, 0);
+    };
+    float2 ax = f2s(0.0f), ay = ax, az = ax;
+    const float cut = P.m2_cut, tol = P.fz_gc_tol;
+    // one batch of four entries (an 8-byte word of the list)
+    auto batch = [&](const uint2 q) {
+        const uint32_t c0 = q.x & 0xffffu, c1 = q.x >> 16, c2 = q.y & 0xffffu, c3 = q.y >> 16;
+        // (rows past this lane's list hold the build's padding entry: a candidate 1e18 away)
+        const uint32_t t0 = c0 & 0xfffu, t1 = c1 & 0xfffu, t2 = c2 & 0xfffu, t3 = c3 & 0xfffu;
+        const FastPair2 fa = fast_gate2(P, F, f2(tx[t0], tx[t1]), f2(ty[t0], ty[t1]), f2(tz[t0], tz[t1]));
+        const FastPair2 fb = fast_gate2(P, F, f2(tx[t2], tx[t3]), f2(ty[t2], ty[t3]), f2(tz[t2], tz[t3]));
+        const bool tiny = !(fminf(fminf(fa.m2.x, fa.m2.y), fminf(fb.m2.x, fb.m2.y)) >= 1e-12f);
+        const bool i0 = !(fa.m2.x >= cut) && !tiny, i1 = !(fa.m2.y >= cut) && !tiny;  // (NaN: in, then unsure)
+        const bool i2 = !(fb.m2.x >= cut) && !tiny, i3 = !(fb.m2.y >= cut) && !tiny;
+        const bool p0 = i0 && fa.gc.x > tol, p1 = i1 && fa.gc.y > tol, p2 = i2 && fb.gc.x > tol, p3 = i3 && fb.gc.y > tol;
+        const bool u0 = i0 && !(fabsf(fa.gc.x) > tol), u1 = i1 && !(fabsf(fa.gc.y) > tol);
+        const bool u2 = i2 && !(fabsf(fb.gc.x) > tol), u3 = i3 && !(fabsf(fb.gc.y) > tol);
+        if (p0 || p1) fast_force2(P, F, fa, p0, p1, vel_of(c0, p0), vel_of(c1, p1), ax, ay, az);
+        if (p2 || p3) fast_force2(P, F, fb, p2, p3, vel_of(c2, p2), vel_of(c3, p3), ax, ay, az);
+        if (tiny || u0 || u1 || u2 || u3) {
+            // guard band / degenerate pair (rare): the reference's own sequence decides and evaluates
+            // (which entries: the flags taken above, not a second evaluation of the cosine -- the
+            //  compiler may fuse the two differently, and an entry must go exactly one way)
+            const uint32_t open_mask = tiny ? 0xfu : (u0 ? 1u : 0u) | (u1 ? 2u : 0u) | (u2 ? 4u : 0u) | (u3 ? 8u : 0u);
+#pragma unroll 1
+            for (uint32_t u = 0; u < 4; ++u) {
+                if (!(open_mask >> u & 1u)) continue;
+                const uint32_t cu = u == 0 ? c0 : u == 1 ? c1 : u == 2 ? c2 : c3;
+                const uint32_t tu = cu & 0xfffu;
+                const float dx = fsub(tx[tu], self.p.x), dy = fsub(ty[tu], self.p.y), dz = fsub(tz[tu], self.p.z);
+                const float m2 = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));  // (the same bits as above)
+                if (m2 >= cut) continue;
+                const float4 vj = vel_of(cu, true);
+                V3 contrib;
+                if (pair_inrange<false>(P, self, v3(dx, dy, dz), m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar, contrib)) {
+                    ax.x += contrib.x;
+                    ay.x += contrib.y;
+                    az.x += contrib.z;
+                }
+            }
+        }
+    };
+    // four words of entries in flight; the loop is unrolled by four so that they need no rotation
+    uint2 q2 = make_uint2(0, 0), q3 = q2;
+    if (8 < nmax) q2 = __ldcs(vlp + 2 * NL_BLOCK);
+    if (12 < nmax) q3 = __ldcs(vlp + 3 * NL_BLOCK);
+    const uint2 *nxt = vlp + 4 * NL_BLOCK;  // word of entries k + 16 ..
+#pragma unroll 1
+    for (uint32_t k = 0; k < nmax; k += 16, nxt += 4 * NL_BLOCK) {
+        const uint2 w0 = q0, w1 = q1, w2 = q2, w3 = q3;
+        if (k + 16 < nmax) q0 = __ldcs(nxt);
+        if (k + 20 < nmax) q1 = __ldcs(nxt + NL_BLOCK);
+        if (k + 24 < nmax) q2 = __ldcs(nxt + 2 * NL_BLOCK);
+        if (k + 28 < nmax) q3 = __ldcs(nxt + 3 * NL_BLOCK);
+        batch(w0);
+        if (k + 4 < nmax) batch(w1);
+        if (k + 8 < nmax) batch(w2);
+        if (k + 12 < nmax) batch(w3);
+    }
+    ax_out = ax.x + ax.y;
+    ay_out = ay.x + ay.y;
+    az_out = az.x + az.y;
 }
 
 template <int TAP>
 __global__ void __launch_bounds__(NL_BLOCK, 5)
 nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO nl, unsigned *__restrict__ status,
                TapOut tap) {
-    if (TAP == TAP_STEP && io.ctl && io.ctl->stale) return;  // lazy re-binning: this step is void
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    NlFastSmem &S = *reinterpret_cast<NlFastSmem *>(smem_raw);
+    float *const tile = reinterpret_cast<float *>(smem_raw);
+    NlFastTail &S = *reinterpret_cast<NlFastTail *>(smem_raw + sizeof(float) * NF_SMEM_FLOATS);
     const uint32_t tid = threadIdx.x;
     const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
     const bool active = s < io.last;
-    const uint32_t *const tab = nl.cta_tab + (size_t)blockIdx.x * NL_CTA_WORDS;
-    const bool no_lists = __ldg(tab + 18) != 0u;
-    if (tid < 32 && !no_lists) {  // warp 0 gets the tile moving before anything else
+    const NlPrologue pro = nl_prologue<TAP == TAP_STEP, true>(io, nl, tid, s, active);
+    const uint32_t no_lists = pro.no_lists, ub = pro.ub, ue = pro.ue;
+    const float4 pi4 = pro.pi4, vi4 = pro.vi4;
+    const uint32_t n_c = pro.n_c;
+    if (pro.stale) return;  // lazy re-binning: this step is void (nothing staged, nothing written yet)
+
+    bool form_b = false;
+    if (tid < 32 && !no_lists) {  // warp 0 gets the tile moving
         if (tid == 0) mbar_init(&S.bar, 1);
         __syncwarp();
-        const uint32_t ub = tid < 9 ? __ldg(tab + tid) : 0u, ue = tid < 9 ? __ldg(tab + 9 + tid) : 0u;
-        nl_stage(S, tid, ub, ue, io.soa_in[0], io.soa_in[1], io.soa_in[2], NF_TILE, S.tv, io.vel_s);
+        const uint32_t len = ue - ub;
+        uint32_t inc = len;  // inclusive prefix sum over the lanes
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+            if ((int)tid >= off) inc += t;
+        }
+        const uint32_t toff = inc - len, total = __shfl_sync(0xffffffffu, inc, 8);
+        form_b = total > (uint32_t)NF_TILE;  // (a layout with lists fits form B: the build checked)
+        if (tid < 9) {
+            S.toff[tid] = toff;
+            S.tslot[tid] = ub - toff;
+        }
+        if (tid == 0) {
+            S.toff[9] = total;
+            if (total) mbar_expect_tx(&S.bar, total * (form_b ? 12u : 28u));
+        }
+        __syncwarp();
+        if (tid < 9 && len) {
+            const int stride = form_b ? NF_STRIDE_B : NF_STRIDE_A;
+            bulk_g2s(tile + toff, io.soa_in[0] + ub, len * 4u, &S.bar);
+            bulk_g2s(tile + stride + toff, io.soa_in[1] + ub, len * 4u, &S.bar);
+            bulk_g2s(tile + 2 * stride + toff, io.soa_in[2] + ub, len * 4u, &S.bar);
+            if (!form_b) bulk_g2s(reinterpret_cast<float4 *>(tile + 3 * NF_STRIDE_A) + toff, io.vel_s + ub, len * 16u, &S.bar);
+        }
+        // the padding entries' "candidate": the slot just past the form's tile
+        if (tid == 9) {
+            const int stride = form_b ? NF_STRIDE_B : NF_STRIDE_A;
+            tile[stride - 8] = tile[2 * stride - 8] = tile[3 * stride - 8] = 1e18f;
+        }
     }
-    if (tid == 32) S.tx[NF_TILE] = S.ty[NF_TILE] = S.tz[NF_TILE] = 1e18f;  // the padding entries' "candidate"
-
-    float4 pi4 = make_float4(0, 0, 0, 0), vi4 = make_float4(0, 0, 0, 0);
-    uint32_t n_c = 0;
-    if (active) {
-        pi4 = io.pos_s[s];
-        vi4 = io.vel_s[s];
-        n_c = __ldg(nl.count + (s - io.first));
-    }
-    // (four entries per 8-byte word; two batches in flight)
-    const uint2 *const vlp = reinterpret_cast<const uint2 *>(nl.entries) + (size_t)blockIdx.x * (nl.vcap / 4) * NL_BLOCK + tid;
-    uint2 q0 = __ldcs(vlp), q1 = __ldcs(vlp + NL_BLOCK);
     if (TAP == TAP_STEP && io.ctl) track_motion(io.ctl, active, pi4, vi4);
     Self self;
     self.p = self.v = self.vhat = v3zero();
@@ -509,44 +731,14 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     }
     __syncthreads();  // the barrier is initialised, the layout is in shared memory
     const uint32_t nmax = __reduce_max_sync(0xffffffffu, n_c);
-    if (S.toff[9] > 0) mbar_wait(&S.bar, 0);
-
-    float ax = 0.0f, ay = 0.0f, az = 0.0f;
-#pragma unroll 1
-    for (uint32_t k = 0; k < nmax; k += 4) {
-        const uint32_t c[4] = {q0.x & 0xffffu, q0.x >> 16, q0.y & 0xffffu, q0.y >> 16};
-        q0 = q1;
-        if (k + 8 < nmax) q1 = __ldcs(vlp + (size_t)(k / 4 + 2) * NL_BLOCK);
-        FastPair f[4];
-        uint32_t t[4];
-        bool any_unsure = false;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            t[u] = c[u] & 0xfffu;  // (rows past this lane's list hold the build's padding entry)
-            f[u] = fast_gate(P, self, S.tx[t[u]], S.ty[t[u]], S.tz[t[u]]);
-            any_unsure |= f[u].unsure;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (f[u].pass) fast_force(P, self, f[u], S.tv[t[u]], ax, ay, az);
-        if (any_unsure) {
-            // guard band / degenerate pair (rare): the reference's own sequence decides and evaluates
-#pragma unroll 1
-            for (uint32_t u = 0; u < 4; ++u) {
-                const uint32_t tu = (u == 0 ? c[0] : u == 1 ? c[1] : u == 2 ? c[2] : c[3]) & 0xfffu;
-                const FastPair fu = fast_gate(P, self, S.tx[tu], S.ty[tu], S.tz[tu]);
-                if (!fu.unsure) continue;
-                const float4 vj = S.tv[tu];
-                V3 contrib;
-                if (pair_inrange<false>(P, self, v3(fu.dx, fu.dy, fu.dz), fu.m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar,
-                                        contrib)) {
-                    ax += contrib.x;
-                    ay += contrib.y;
-                    az += contrib.z;
-                }
-            }
-        }
-    }
+    const uint32_t total = S.toff[9];
+    if (total > 0) mbar_wait(&S.bar, 0);
+    nl_warm_successor<true>(pro, io, nl, tid, true);
+    float ax, ay, az;
+    if (total > (uint32_t)NF_TILE)
+        fast_entries<true>(P, self, S.tslot, io.vel_s, pro.vlp, nmax, pro.q0, pro.q1, ax, ay, az);
+    else
+        fast_entries<false>(P, self, S.tslot, io.vel_s, pro.vlp, nmax, pro.q0, pro.q1, ax, ay, az);
     if (!active) return;
     if (!work) ax = ay = az = 0.0f;  // (steering overrides, ghost record: the lists were walked for nothing)
     walk_finish<TAP, true>(P, s, pi4, vi4, self, v3(ax, ay, az), 0u, 0ull, io, status, tap);
@@ -562,18 +754,52 @@ size_t nl_cta_tab_elems(uint32_t rows) {
     return (((size_t)rows + NL_BLOCK - 1) / NL_BLOCK) * NL_CTA_WORDS;
 }
 uint32_t nl_tile_cap(bool fast) { return fast ? NF_TILE : NL_TILE; }
+uint32_t nl_tile_cap_b(bool fast) { return fast ? NF_TILE_B : 0; }
+// CTAs of a list walk that are resident on the current device at once (0 if that cannot be told)
+uint32_t nl_walk_resident_ctas(bool fast) {
+    static uint32_t cached[2] = {~0u, ~0u};
+    uint32_t &c = cached[fast ? 1 : 0];
+    if (c == ~0u) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) {
+            if (fast) {
+                const int smem = (int)(sizeof(float) * NF_SMEM_FLOATS + sizeof(NlFastTail));
+                e = cudaFuncSetAttribute(nl_fast_kernel<TAP_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                if (e == cudaSuccess)
+                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nl_fast_kernel<TAP_STEP>, NL_BLOCK, smem);
+            } else {
+                const int smem = (int)sizeof(NlWalkSmem);
+                e = cudaFuncSetAttribute(nl_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nl_walk_kernel, NL_BLOCK, smem);
+            }
+        }
+        if (e != cudaSuccess) (void)cudaGetLastError();
+        c = e == cudaSuccess ? (uint32_t)(sms * per_sm) : 0u;
+    }
+    return c;
+}
 
 int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl) {
     if (io.last <= io.first) return FP_OK;
     const uint32_t ctas = (io.last - io.first + NL_BLOCK - 1) / NL_BLOCK;
+    if (nl.tile_cap_b > (uint32_t)NF_TILE_B || (!nl.tile_cap_b && nl.tile_cap > (uint32_t)NL_TILE)) {
+        set_error("internal: candidate-list tile capacity");
+        return FP_ERR_INVALID;
+    }
     if (nl.vis_first) {
-        const int smem = (int)(sizeof(NlBuildSmem) + sizeof(uint16_t) * NB_TMP * NL_BLOCK);
-        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        nl_build_kernel<true><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+        const int smem = (int)(sizeof(NlBuildSmem<NF_TILE_B>) + sizeof(uint16_t) * NB_TMP * NL_BLOCK);
+        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<true, NF_TILE_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        nl_build_kernel<true, NF_TILE_B><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+    } else if (nl.tile_cap_b) {
+        const int smem = (int)sizeof(NlBuildSmem<NF_TILE_B>);
+        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<false, NF_TILE_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        nl_build_kernel<false, NF_TILE_B><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
     } else {
-        const int smem = (int)sizeof(NlBuildSmem);
-        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        nl_build_kernel<false><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
+        const int smem = (int)sizeof(NlBuildSmem<NL_TILE>);
+        FP_CUDA(cudaFuncSetAttribute(nl_build_kernel<false, NL_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        nl_build_kernel<false, NL_TILE><<<ctas, NL_BLOCK, smem, st>>>(g, io, nl);
     }
     count_launch();
     FP_CUDA(cudaGetLastError());
@@ -585,7 +811,7 @@ int launch_nl_walk(cudaStream_t st, const DevParams &P, const GridDesc &g, int t
     if (io.last <= io.first) return FP_OK;
     const uint32_t ctas = (io.last - io.first + NL_BLOCK - 1) / NL_BLOCK;
     if (P.numerics_fast) {
-        const int smem = (int)sizeof(NlFastSmem);
+        const int smem = (int)(sizeof(float) * NF_SMEM_FLOATS + sizeof(NlFastTail));
         if (tap == TAP_STEP) {
             FP_CUDA(cudaFuncSetAttribute(nl_fast_kernel<TAP_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             nl_fast_kernel<TAP_STEP><<<ctas, NL_BLOCK, smem, st>>>(P, g, io, nl, status, tap_out);

@@ -47,8 +47,8 @@ def main():
     orc = oracle()
     nt = max(1, (os.cpu_count() or 1) // world)
     c = orc.default_config()
-    if os.environ.get("MGPU_ONLY") == "lazy":
-        lazy_slabs(orc, c, rank, world, local, nt)
+    if os.environ.get("MGPU_ONLY") in ("lazy", "fast"):
+        (lazy_slabs if os.environ["MGPU_ONLY"] == "lazy" else fast_numerics)(orc, c, rank, world, local, nt)
         dist.barrier()
         dist.destroy_process_group()
         if rank == 0:
@@ -153,7 +153,11 @@ def fast_numerics(orc, c, rank, world, local, nt):
               flush=True)
     n = 80000
     st = synth.uniform_flock(n, 380.0, seed=86)
-    sim, sc = make(st, _lib.METHOD_GRID, c, TABLES, local, _lib.NUMERICS_FAST)
+    # (walls outside the flock: TABLES' own box ends at 200, in the middle of this one -- its 1 / d^2
+    #  singularity shoots boids across a whole slab in one step once the slabs are 3 cell layers thin
+    #  (8 ranks), which the library reports as FP_STATUS_SLAB_JUMP, as it should)
+    tables = dict(TABLES, bbox=np.array([-60, 440, -60, 440, -60, 440], np.float32))
+    sim, sc = make(st, _lib.METHOD_GRID, c, tables, local, _lib.NUMERICS_FAST)
     sim.set_rebin(skin=0.12)
     ga = sim.read_accel()
     gc, gh = sim.read_neighbors()
