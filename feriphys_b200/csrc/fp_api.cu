@@ -171,12 +171,30 @@ bool nl_enabled();  // candidate lists (below): FP_NL=0 turns them off
 
 // every entry point except fp_flock_step: the handle must be valid and every enqueued step
 // must be known to have happened (lazy re-binning may have voided some: settle replays them)
-int check(fp_flock *f, bool settled = true) {
+// rows left in a pinned slot by fp_flock_write_state become the device state (one kernel reading
+// mapped host memory: no copy engine involved)
+int ingest_pending(fp_flock *f) {
+    if (!f->pending_aos) return FP_OK;
+    int rc = launch_aos6_to_soa(f->stream, f->pending_aos, f->pos[f->cur], f->vel[f->cur], f->n, f->first_index);
+    if (rc) return rc;
+    FP_CUDA(cudaEventRecord(f->up_ev[f->pending_slot], f->stream));
+    f->pending_aos = nullptr;
+    return FP_OK;
+}
+
+// keep_io: the caller deals with rows pending in a pinned slot and with the mapped output rows
+// itself (fp_flock_step, fp_flock_read_state); everybody else sees plain device state
+int check(fp_flock *f, bool settled = true, bool keep_io = false) {
     if (!f) {
         set_error("null flock handle");
         return FP_ERR_INVALID;
     }
     FP_CUDA(cudaSetDevice(f->device));
+    if (!keep_io) {
+        f->out_valid = false;
+        int rc = ingest_pending(f);
+        if (rc) return rc;
+    }
     return settled ? settle(f) : FP_OK;
 }
 
@@ -540,13 +558,6 @@ bool nl_enabled() {
     }();
     return on;
 }
-bool nl_prefetch_enabled() {  // FP_NL_PREFETCH=0: no L2 warming for the CTA that comes next
-    static const bool on = [] {
-        const char *e = getenv("FP_NL_PREFETCH");
-        return !(e && e[0] == '0');
-    }();
-    return on;
-}
 bool nl_trace() {
     static const bool on = getenv("FP_NL_TRACE") != nullptr;
     return on;
@@ -609,7 +620,6 @@ NlIO nl_io(const fp_flock *f, double skins = 1.0) {
     nl.vcap = NL_VCAP;
     nl.tile_cap = nl_tile_cap(f->P.numerics_fast != 0);
     nl.tile_cap_b = nl_tile_cap_b(f->P.numerics_fast != 0);
-    nl.ahead = nl_prefetch_enabled() ? nl_walk_resident_ctas(f->P.numerics_fast != 0) : 0u;
     // every pair within reach while the binning stands was within reach + skin when it was made
     // (skins = 2: within reach + 2 skin at any other moment of the binning's life)
     const double R = (double)reach_of(f->cfg) + skins * (double)f->grid.skin;
@@ -975,6 +985,7 @@ int fp_flock_destroy(fp_flock *f) {
     if (f->d_stage) cudaFree(f->d_stage);
     for (int k = 0; k < 2; ++k) {
         if (f->h_up[k]) cudaFreeHost(f->h_up[k]);
+        if (k == 0 && f->h_out) cudaFreeHost(f->h_out);
         if (f->up_ev[k]) cudaEventDestroy(f->up_ev[k]);
     }
     if (f->h_ctl) cudaFreeHost(f->h_ctl);
@@ -1203,12 +1214,14 @@ extern "C" {
 int fp_flock_step(fp_flock *f, uint32_t nsteps) {
     // grid steps keep running ahead of the host: no settle here (grid_steps / shard_step do it
     // when they need to); the other methods start from a settled state
-    int rc = check(f, false);
+    int rc = check(f, false, true);
     if (rc) return rc;
     if (nsteps == 0) return FP_OK;
+    f->out_valid = false;
     if (f->timing) f->timed_steps += nsteps;
+    const int m = f->shard ? FP_METHOD_AUTO : resolve_method(f);
+    if (m != FP_METHOD_SMALL && (rc = ingest_pending(f))) return rc;
     if (f->shard) return shard_step(f->shard, f, nsteps);
-    const int m = resolve_method(f);
     if (f->n == 0) return FP_OK;
     if (m == FP_METHOD_GRID) return grid_steps(f, nsteps);
     if ((rc = settle(f))) return rc;
@@ -1227,9 +1240,24 @@ int fp_flock_step(fp_flock *f, uint32_t nsteps) {
             P.leads = rows;
         }
         if ((rc = mark(f)) || (rc = mark(f))) return rc;
+        const size_t out_bytes = (size_t)f->n * 6 * sizeof(float);
+        if (f->h_out_bytes < out_bytes) {
+            if (f->h_out) cudaFreeHost(f->h_out);
+            f->h_out = nullptr;
+            f->h_out_bytes = 0;
+            FP_CUDA(cudaHostAlloc((void **)&f->h_out, out_bytes, cudaHostAllocMapped));
+            f->h_out_bytes = out_bytes;
+        }
+        float *d_out = nullptr;
+        FP_CUDA(cudaHostGetDevicePointer((void **)&d_out, f->h_out, 0));
         rc = launch_small(f->stream, P, f->pos[f->cur], f->vel[f->cur], f->n, nsteps, rows, nrows,
-                          f->d_status);
+                          f->d_status, f->pending_aos, d_out, f->first_index);
         if (rc) return rc;
+        if (f->pending_aos) {  // the slot is free again once this launch has run
+            FP_CUDA(cudaEventRecord(f->up_ev[f->pending_slot], f->stream));
+            f->pending_aos = nullptr;
+        }
+        f->out_valid = true;
         if ((rc = mark(f))) return rc;
         f->table_cursor += nsteps;
         return FP_OK;
@@ -1303,12 +1331,18 @@ int fp_flock_status(fp_flock *f, uint32_t *flags) {
 }
 
 int fp_flock_read_state(fp_flock *f, float *out) {
-    int rc = check(f);
+    int rc = check(f, true, true);
     if (rc) return rc;
+    if ((rc = ingest_pending(f))) return rc;
     if (f->shard) return shard_read_state(f->shard, f, out);
     if (!f->n) return FP_OK;
     if (!out) { set_error("null output"); return FP_ERR_INVALID; }
     const size_t bytes = (size_t)f->n * 6 * sizeof(float);
+    if (f->out_valid && f->h_out) {  // the last small step left the rows in mapped memory
+        FP_CUDA(cudaStreamSynchronize(f->stream));
+        memcpy(out, f->h_out, bytes);
+        return FP_OK;
+    }
     if ((rc = ensure_stage(f, bytes))) return rc;
     if ((rc = launch_soa_to_aos6(f->stream, f->pos[f->cur], f->vel[f->cur], (float *)f->d_stage, f->n,
                                  f->first_index, 1)))
@@ -1326,25 +1360,27 @@ int fp_flock_write_state(fp_flock *f, const float *state) {
     if (!state) { set_error("null state"); return FP_ERR_INVALID; }
     const size_t bytes = (size_t)f->n * 6 * sizeof(float);
     if ((rc = ensure_stage(f, bytes))) return rc;
-    const bool small = bytes <= fp_flock::SMALL_UPLOAD;
-    const void *src = state;
-    uint32_t slot = 0;
-    if (small) {  // copy the caller's buffer out now; the device picks it up when it gets there
-        slot = f->up_cur++ & 1u;
+    if (bytes <= fp_flock::SMALL_UPLOAD) {
+        // copy the caller's buffer out now; the device picks the rows up from the pinned slot when it
+        // gets there -- the single-CTA step kernel itself, or a conversion kernel before anything else
+        const uint32_t slot = f->up_cur++ & 1u;
         if (!f->h_up[slot]) {
-            FP_CUDA(cudaMallocHost(&f->h_up[slot], fp_flock::SMALL_UPLOAD));
+            FP_CUDA(cudaHostAlloc(&f->h_up[slot], fp_flock::SMALL_UPLOAD, cudaHostAllocMapped));
             FP_CUDA(cudaEventCreateWithFlags(&f->up_ev[slot], cudaEventDisableTiming));
         }
-        FP_CUDA(cudaEventSynchronize(f->up_ev[slot]));  // the upload that last used this slot
+        FP_CUDA(cudaEventSynchronize(f->up_ev[slot]));  // the kernel that last read this slot
         memcpy(f->h_up[slot], state, bytes);
-        src = f->h_up[slot];
+        void *dptr = nullptr;
+        FP_CUDA(cudaHostGetDevicePointer(&dptr, f->h_up[slot], 0));
+        f->pending_aos = (const float *)dptr;
+        f->pending_slot = slot;
+    } else {
+        FP_CUDA(cudaMemcpyAsync(f->d_stage, state, bytes, cudaMemcpyHostToDevice, f->stream));
+        if ((rc = launch_aos6_to_soa(f->stream, (const float *)f->d_stage, f->pos[f->cur], f->vel[f->cur],
+                                     f->n, f->first_index)))
+            return rc;
+        FP_CUDA(cudaStreamSynchronize(f->stream));  // the caller's buffer is not retained
     }
-    FP_CUDA(cudaMemcpyAsync(f->d_stage, src, bytes, cudaMemcpyHostToDevice, f->stream));
-    if ((rc = launch_aos6_to_soa(f->stream, (const float *)f->d_stage, f->pos[f->cur], f->vel[f->cur],
-                                 f->n, f->first_index)))
-        return rc;
-    if (small) FP_CUDA(cudaEventRecord(f->up_ev[slot], f->stream));
-    else FP_CUDA(cudaStreamSynchronize(f->stream));  // the caller's buffer is not retained
     f->permuted = false;
     f->bin_valid = false;
     f->nl_off = false;

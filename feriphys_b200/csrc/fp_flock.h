@@ -84,6 +84,15 @@ struct fp_flock {
     void *h_up[2] = {nullptr, nullptr};
     cudaEvent_t up_ev[2] = {nullptr, nullptr};
     uint32_t up_cur = 0;
+    // Demo-sized flocks on the single-CTA kernel skip the copies altogether: fp_flock_write_state
+    // leaves the caller's rows in the pinned (device-mapped) slot, the step kernel reads them from
+    // there and writes the advanced rows to a second mapped buffer, fp_flock_read_state waits for the
+    // stream and copies them out -- one launch and one synchronisation per write / step / read round.
+    const float *pending_aos = nullptr;  // rows handed over by write_state that no kernel has ingested yet
+    uint32_t pending_slot = 0;
+    float *h_out = nullptr;              // pinned, mapped: caller-order rows written by the last small step
+    size_t h_out_bytes = 0;
+    bool out_valid = false;              // h_out describes the current state
     // timing hook: three events per step (before sort phase, before influence, after)
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;

@@ -122,8 +122,11 @@ int launch_allpairs(cudaStream_t st, const DevParams &P, int tap, const float4 *
 
 // One CTA, `nsteps` steps in one launch, reference summation order (fp_small.cu).
 // lead_table: nsteps rows of n_leads x 8 floats, or NULL to use P.leads for every step.
+// aos_in (may be null): the state comes from these caller-order rows [px py pz vx vy vz] (mapped host
+// memory) instead of pos / vel; aos_out (may be null): the advanced rows are also written there.
 int launch_small(cudaStream_t st, const DevParams &P, float4 *pos, float4 *vel, uint32_t n,
-                 uint32_t nsteps, const float *lead_table, uint32_t lead_rows, unsigned *status);
+                 uint32_t nsteps, const float *lead_table, uint32_t lead_rows, unsigned *status,
+                 const float *aos_in = nullptr, float *aos_out = nullptr, uint32_t first_index = 0);
 uint32_t small_max_boids();
 
 // ---- grid (fp_grid.cu, fp_sort.cu) -----------------------------------------
@@ -171,7 +174,6 @@ struct NlIO {
     uint32_t vcap;       // list capacity, a multiple of 4
     uint32_t tile_cap;   // staged candidates the walk that will use the lists can hold per CTA
     uint32_t tile_cap_b; // ... in its positions-only form (fast walk; 0: there is no such form)
-    uint32_t ahead;      // walk: CTAs resident on the device at once -- CTA b warms L2 for CTA b + ahead (0: off)
     float m2_wide;       // build cut: (reach + skin)^2 (1 + 1e-5)
     int vis_first;       // order each list with the entries predicted to be in view first (fast walk)
     float vis_c;         // ... in view <=> cosine of the sight angle > vis_c
@@ -180,7 +182,6 @@ size_t nl_entries_elems(uint32_t rows, uint32_t vcap);
 size_t nl_cta_tab_elems(uint32_t rows);
 uint32_t nl_tile_cap(bool fast);
 uint32_t nl_tile_cap_b(bool fast);
-uint32_t nl_walk_resident_ctas(bool fast);
 // after a binning, before the first walk that uses the lists
 int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl);
 // a step (TAP_STEP) -- or, under FAST numerics, the acceleration tap -- on the standing lists.

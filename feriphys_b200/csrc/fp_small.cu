@@ -20,10 +20,39 @@ constexpr int SM_BATCH = 4;
 
 uint32_t small_max_boids() { return SM_MAX; }
 
+// A boid of the single-CTA kernels comes from the device arrays or, when fp_flock_write_state left
+// the caller's rows in mapped host memory, straight from there (the same conversion as
+// aos6_to_soa_kernel: caller order is internal order for these flocks); it goes back to the device
+// arrays and, for fp_flock_read_state, to mapped host memory as a caller-order row.
+__device__ __forceinline__ void small_load(const float4 *gpos, const float4 *gvel, const float *aos_in,
+                                           uint32_t first_index, uint32_t i, float4 &p, float4 &v) {
+    if (aos_in) {
+        const float2 *r = reinterpret_cast<const float2 *>(aos_in + 6ull * i);  // (rows are 8-byte aligned)
+        const float2 a = r[0], b = r[1], c = r[2];
+        p = make_float4(a.x, a.y, b.x, __uint_as_float(first_index + i));
+        v = make_float4(b.y, c.x, c.y, 0.0f);
+    } else {
+        p = gpos[i];
+        v = gvel[i];
+    }
+}
+__device__ __forceinline__ void small_store(float4 *gpos, float4 *gvel, float *aos_out, uint32_t i, float4 p,
+                                            float4 v) {
+    gpos[i] = p;
+    gvel[i] = v;
+    if (aos_out) {
+        float2 *r = reinterpret_cast<float2 *>(aos_out + 6ull * i);
+        r[0] = make_float2(p.x, p.y);
+        r[1] = make_float2(p.z, v.x);
+        r[2] = make_float2(v.y, v.z);
+    }
+}
+
 __global__ void __launch_bounds__(SM_THREADS, 1)
 small_kernel(const DevParams P, float4 *__restrict__ gpos, float4 *__restrict__ gvel, uint32_t n,
              uint32_t nsteps, const float *__restrict__ lead_table, uint32_t lead_rows,
-             unsigned *__restrict__ status) {
+             unsigned *__restrict__ status, const float *__restrict__ aos_in, float *__restrict__ aos_out,
+             uint32_t first_index) {
     __shared__ float4 spos[2][SM_MAX + SM_BATCH];
     __shared__ float4 svel[2][SM_MAX + SM_BATCH];
     const uint32_t i = threadIdx.x;
@@ -31,8 +60,7 @@ small_kernel(const DevParams P, float4 *__restrict__ gpos, float4 *__restrict__ 
     for (int b = 0; b < 2; ++b)  // padding read by the masked tail of the last batch
         if (i < SM_BATCH) spos[b][SM_MAX + i] = svel[b][SM_MAX + i] = make_float4(0, 0, 0, 0);
     if (mine) {
-        spos[0][i] = gpos[i];
-        svel[0][i] = gvel[i];
+        small_load(gpos, gvel, aos_in, first_index, i, spos[0][i], svel[0][i]);
     } else {
         spos[0][i] = svel[0][i] = spos[1][i] = svel[1][i] = make_float4(0, 0, 0, 0);
     }
@@ -94,10 +122,7 @@ small_kernel(const DevParams P, float4 *__restrict__ gpos, float4 *__restrict__ 
         cur ^= 1;
     }
     __syncthreads();
-    if (mine) {
-        gpos[i] = spos[cur][i];
-        gvel[i] = svel[cur][i];
-    }
+    if (mine) small_store(gpos, gvel, aos_out, i, spos[cur][i], svel[cur][i]);
     if (flags) atomicOr(status, flags);
 }
 
@@ -125,15 +150,13 @@ struct Small2Smem {
 __global__ void __launch_bounds__(S2_THREADS, 1)
 small2_kernel(const DevParams P, float4 *__restrict__ gpos, float4 *__restrict__ gvel, uint32_t n,
               uint32_t nsteps, const float *__restrict__ lead_table, uint32_t lead_rows,
-              unsigned *__restrict__ status) {
+              unsigned *__restrict__ status, const float *__restrict__ aos_in, float *__restrict__ aos_out,
+              uint32_t first_index) {
     extern __shared__ __align__(16) unsigned char s2_raw[];
     Small2Smem &S = *reinterpret_cast<Small2Smem *>(s2_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t i = tid / S2_LANES, lane = tid % S2_LANES;
-    if (tid < n) {
-        S.pos[0][tid] = gpos[tid];
-        S.vel[0][tid] = gvel[tid];
-    }
+    if (tid < n) small_load(gpos, gvel, aos_in, first_index, tid, S.pos[0][tid], S.vel[0][tid]);
     int cur = 0;
     unsigned flags = 0;
     const int lead_stride = P.n_leads * 8;
@@ -179,15 +202,13 @@ small2_kernel(const DevParams P, float4 *__restrict__ gpos, float4 *__restrict__
         cur ^= 1;
     }
     __syncthreads();
-    if (tid < n) {
-        gpos[tid] = S.pos[cur][tid];
-        gvel[tid] = S.vel[cur][tid];
-    }
+    if (tid < n) small_store(gpos, gvel, aos_out, tid, S.pos[cur][tid], S.vel[cur][tid]);
     if (flags) atomicOr(status, flags);
 }
 
 int launch_small(cudaStream_t st, const DevParams &P, float4 *pos, float4 *vel, uint32_t n,
-                 uint32_t nsteps, const float *lead_table, uint32_t lead_rows, unsigned *status) {
+                 uint32_t nsteps, const float *lead_table, uint32_t lead_rows, unsigned *status,
+                 const float *aos_in, float *aos_out, uint32_t first_index) {
     if (!n || !nsteps) return FP_OK;
     if (n > SM_MAX) {
         set_error("flock too large for the single-CTA kernel");
@@ -201,10 +222,10 @@ int launch_small(cudaStream_t st, const DevParams &P, float4 *pos, float4 *vel, 
         const int smem = (int)sizeof(Small2Smem);
         FP_CUDA(cudaFuncSetAttribute(small2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         small2_kernel<<<1, S2_THREADS, smem, st>>>(P, pos, vel, n, nsteps, lead_rows ? lead_table : nullptr, lead_rows,
-                                                  status);
+                                                  status, aos_in, aos_out, first_index);
     } else {
         small_kernel<<<1, SM_THREADS, 0, st>>>(P, pos, vel, n, nsteps, lead_rows ? lead_table : nullptr, lead_rows,
-                                              status);
+                                              status, aos_in, aos_out, first_index);
     }
     count_launch();
     FP_CUDA(cudaGetLastError());

@@ -47,7 +47,7 @@ constexpr int NL_BLOCK = 128;   // threads (= boids) per CTA, as the plain walk
 constexpr int NL_TILE = 1904;   // staged candidates per CTA (build and exact walk), as the plain walk
 constexpr int NL_CAP = 48;      // survivor list of the exact walk (shared memory): six CTAs per SM
 constexpr int NF_TILE = 1568;   // staged candidates per CTA of the fast walk, form A (positions + velocities)
-constexpr int NF_TILE_B = 3648; // ... form B (positions only)
+constexpr int NF_TILE_B = 2560; // ... form B (positions only; the build kernel stages this many too)
 constexpr int NL_CTA_WORDS = 20;  // cached tile layout per CTA: ub[9], ue[9], [18] = no lists, 1 spare
 
 // this CTA gets no lists: it walks from global memory every step (counted once per CTA)
@@ -55,10 +55,8 @@ __device__ __forceinline__ void nl_no_lists(const NlIO &nl, uint32_t *tab) {
     if (atomicExch(tab + 18, 1u) == 0u) atomicAdd(nl.flag, 1u);
 }
 
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
 __device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t *p) {  // (volatile: issued where it stands)
     uint32_t v;
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -71,19 +69,19 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
 }
 
 // What every list walk starts with.  All loads of the prologue are issued before anything waits on
-// one of them -- the step's validity, the CTA's layout record, the boid, its list length, its first
-// two words of entries -- and, into L2 only, the same items of the CTA that will take this one's
-// place `nl.ahead` blocks on: its prologue then waits for L2, not for HBM (the start-up chain
-// layout -> TMA -> tile was a third of the kernel's stall samples, profiles/r2_c4_nl_fast_v3_*).
+// one of them: the step's validity, the CTA's layout record, the boid, its list length, its first
+// two words of entries (the start-up chain layout -> TMA -> tile was a third of the kernel's stall
+// samples while each link waited for the one before, profiles/r2_c4_nl_fast_v3_*).
+// Measured and dropped: warming L2 for the CTA that will take this one's place (prefetch.global.L2 of
+// its boids and entries, cp.async.bulk.prefetch.L2 of its tile): L2 hits rose from 49 to 63 %, the
+// wait at the start-up barrier did not move, the step lost 5 % (profiles/r2_bench_c4_l2warm.json).
 struct NlPrologue {
     uint32_t stale, no_lists, ub, ue, n_c;
     float4 pi4, vi4;
     const uint2 *vlp;
     uint2 q0, q1;
-    bool pf;            // this CTA warms L2 for a successor
-    uint32_t ub2, ue2;  // the successor's intervals (threads 32 .. 40)
 };
-template <bool STEP, bool EARLY2>  // EARLY2: the successor's intervals are loaded here (two registers), else later
+template <bool STEP>
 __device__ __forceinline__ NlPrologue nl_prologue(const WalkIO &io, const NlIO &nl, uint32_t tid, uint32_t s,
                                                   bool active) {
     NlPrologue p;
@@ -106,46 +104,7 @@ __device__ __forceinline__ NlPrologue nl_prologue(const WalkIO &io, const NlIO &
     p.vlp = reinterpret_cast<const uint2 *>(nl.entries) + (size_t)blockIdx.x * (nl.vcap / 4) * NL_BLOCK + tid;
     p.q0 = __ldcs(p.vlp);
     p.q1 = __ldcs(p.vlp + NL_BLOCK);
-    p.pf = nl.ahead && blockIdx.x + nl.ahead < gridDim.x;
-    p.ub2 = p.ue2 = 0;
-    if (p.pf) {
-        const uint32_t s2 = s + nl.ahead * NL_BLOCK;
-        if (s2 < io.last) {
-            prefetch_l2(io.pos_s + s2);
-            prefetch_l2(io.vel_s + s2);
-        }
-        prefetch_l2(p.vlp + (size_t)nl.ahead * (nl.vcap / 4) * NL_BLOCK);
-        prefetch_l2(p.vlp + (size_t)nl.ahead * (nl.vcap / 4) * NL_BLOCK + NL_BLOCK);
-        if (EARLY2) {
-            if (tid >= 32 && tid < 41) {
-                p.ub2 = ld_nc_u32(tab + (size_t)nl.ahead * NL_CTA_WORDS + (tid - 32));
-                p.ue2 = ld_nc_u32(tab + (size_t)nl.ahead * NL_CTA_WORDS + 9 + (tid - 32));
-            }
-        } else if (tid == 32) {
-            prefetch_l2(tab + (size_t)nl.ahead * NL_CTA_WORDS);
-        }
-    }
     return p;
-}
-// the successor's tile, into L2 (threads 32 .. 40, once this CTA's own tile has landed)
-template <bool EARLY2>
-__device__ __forceinline__ void nl_warm_successor(const NlPrologue &p, const WalkIO &io, const NlIO &nl, uint32_t tid,
-                                                  bool vel) {
-    if (p.pf && tid >= 32 && tid < 41) {
-        uint32_t ub2 = p.ub2, ue2 = p.ue2;
-        if (!EARLY2) {
-            const uint32_t *const tab2 = nl.cta_tab + ((size_t)blockIdx.x + nl.ahead) * NL_CTA_WORDS;
-            ub2 = ld_nc_u32(tab2 + (tid - 32));
-            ue2 = ld_nc_u32(tab2 + 9 + (tid - 32));
-        }
-        if (ue2 > ub2) {
-            const uint32_t bytes = (ue2 - ub2) * 4u;
-            bulk_prefetch_l2(io.soa_in[0] + ub2, bytes);
-            bulk_prefetch_l2(io.soa_in[1] + ub2, bytes);
-            bulk_prefetch_l2(io.soa_in[2] + ub2, bytes);
-            if (vel) bulk_prefetch_l2(io.vel_s + ub2, bytes * 4u);
-        }
-    }
 }
 
 // Lays the nine CTA-wide intervals (ub, ue: multiples of 4, empty = 0, 0) out in the tile and
@@ -417,7 +376,7 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     const uint32_t tid = threadIdx.x;
     const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
     const bool active = s < io.last;
-    const NlPrologue pro = nl_prologue<true, false>(io, nl, tid, s, active);
+    const NlPrologue pro = nl_prologue<true>(io, nl, tid, s, active);
     if (pro.stale) return;  // lazy re-binning: this step is void (nothing staged, nothing written yet)
     const bool no_lists = pro.no_lists != 0u;
     if (tid < 32 && !no_lists) {  // warp 0 gets the tile moving
@@ -450,12 +409,13 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     const uint32_t t_self = work ? s - S.tslot[4] : 0xffffu;
     const uint32_t nmax = __reduce_max_sync(0xffffffffu, n_c);
     if (S.toff[9] > 0) mbar_wait(&S.bar, 0);  // (a layout with lists always fits the tile)
-    nl_warm_successor<false>(pro, io, nl, tid, false);
 
     uint16_t *const lst = &S.list[0][tid];  // entry k at lst[k * BLOCK]
     int cnt = 0;
     uint32_t base = 0;  // warp-uniform progress through the cached lists, a multiple of 4
-    const float kh = P.fov_kh, kl = P.fov_kl;
+    const float2 kh2 = f2s(P.fov_kh), kl2 = f2s(P.fov_kl);
+    const float2 nsx = f2s(-self.p.x), nsy = f2s(-self.p.y), nsz = f2s(-self.p.z);
+    const float2 vhx = f2s(self.vhat.x), vhy = f2s(self.vhat.y), vhz = f2s(self.vhat.z);
 #pragma unroll 1
     for (;;) {
         int room = NL_CAP - (int)__reduce_max_sync(0xffffffffu, (unsigned)cnt);
@@ -473,23 +433,31 @@ nl_walk_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
             const uint32_t c[4] = {q0.x & 0xffffu, q0.x >> 16, q0.y & 0xffffu, q0.y >> 16};
             q0 = q1;
             if (k + 8 < nmax) q1 = __ldcs(vlp + (size_t)(k / 4 + 2) * NL_BLOCK);  // (rows < vcap: a multiple of 4)
-            // The plain walk's pre-gate (fp_walk.cu), one candidate per lane-slot: fused squared
-            // distance against m2_cut_hi, and the conservative FOV test KL m2 < q |q| < KH m2
-            // (drops only pairs culled with a 1e-5 margin; NaN never drops).
-            float mm[4], ss[4];
+            // The plain walk's pre-gate (fp_walk.cu) on packed FP32 -- two entries per FADD2 / FMUL2 /
+            // FFMA2: fused squared distance against m2_cut_hi, and the conservative FOV test
+            // KL m2 < q |q| < KH m2 (drops only pairs culled with a 1e-5 margin; NaN never drops).
+            // A superset is all it has to keep: the drain re-tests exactly.
+            const uint32_t t0 = c[0] & 0xfffu, t1 = c[1] & 0xfffu, t2 = c[2] & 0xfffu, t3 = c[3] & 0xfffu;
+            // (entries past n_c hold stale offsets: any 12-bit offset reads inside the tile arrays,
+            //  result unused)
+            const float2 dx01 = __fadd2_rn(f2(S.tx[t0], S.tx[t1]), nsx), dx23 = __fadd2_rn(f2(S.tx[t2], S.tx[t3]), nsx);
+            const float2 dy01 = __fadd2_rn(f2(S.ty[t0], S.ty[t1]), nsy), dy23 = __fadd2_rn(f2(S.ty[t2], S.ty[t3]), nsy);
+            const float2 dz01 = __fadd2_rn(f2(S.tz[t0], S.tz[t1]), nsz), dz23 = __fadd2_rn(f2(S.tz[t2], S.tz[t3]), nsz);
+            const float2 m01 = __ffma2_rn(dz01, dz01, __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01)));
+            const float2 m23 = __ffma2_rn(dz23, dz23, __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23)));
+            const float2 q01 = __ffma2_rn(vhz, dz01, __ffma2_rn(vhy, dy01, __fmul2_rn(vhx, dx01)));
+            const float2 q23 = __ffma2_rn(vhz, dz23, __ffma2_rn(vhy, dy23, __fmul2_rn(vhx, dx23)));
+            const float2 s01 = __fmul2_rn(q01, f2(fabsf(q01.x), fabsf(q01.y)));
+            const float2 s23 = __fmul2_rn(q23, f2(fabsf(q23.x), fabsf(q23.y)));
+            const float2 h01 = __fmul2_rn(kh2, m01), h23 = __fmul2_rn(kh2, m23);
+            const float2 l01 = __fmul2_rn(kl2, m01), l23 = __fmul2_rn(kl2, m23);
+            const float mm[4] = {m01.x, m01.y, m23.x, m23.y};
+            const float ss[4] = {s01.x, s01.y, s23.x, s23.y};
+            const float hh[4] = {h01.x, h01.y, h23.x, h23.y};
+            const float ll[4] = {l01.x, l01.y, l23.x, l23.y};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const uint32_t t = c[u] & 0xfffu;  // (entries past n_c hold stale offsets: any 12-bit
-                                                   //  offset reads inside the tile arrays, result unused)
-                const float dx = S.tx[t] - self.p.x, dy = S.ty[t] - self.p.y, dz = S.tz[t] - self.p.z;
-                mm[u] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                const float q = fmaf(self.vhat.z, dz, fmaf(self.vhat.y, dy, self.vhat.x * dx));
-                ss[u] = q * fabsf(q);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float hh = kh * mm[u], ll = kl * mm[u];
-                if (k + u < n_c && !(mm[u] >= P.m2_cut_hi) && !(ss[u] < hh && ss[u] > ll)) {
+                if (k + u < n_c && !(mm[u] >= P.m2_cut_hi) && !(ss[u] < hh[u] && ss[u] > ll[u])) {
                     lst[w] = (uint16_t)c[u];
                     w += NL_BLOCK;
                 }
@@ -534,8 +502,6 @@ struct FastSelf {
 struct FastPair2 {
     float2 dx, dy, dz, m2, r, gc;
 };
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
 __device__ __forceinline__ FastPair2 fast_gate2(const DevParams &P, const FastSelf &F, float2 px, float2 py,
                                                 float2 pz) {
     FastPair2 f;
@@ -584,54 +550,69 @@ __device__ __forceinline__ void fast_force2(const DevParams &P, const FastSelf &
 // contributes <=> gc > tol (visible, outside the guard band); `unsure` <=> |gc| <= tol or NaN (guard
 // band; coincident positions).  A batch with a pair closer than 1e-6 (the abs_diff_eq! guards of
 // boid.rs:111,121 may apply) is evaluated by the exact sequence altogether.
+// (shared-memory loads by 32-bit address: through a generic pointer the compiler rebuilt the shared
+//  window base -- S2R CgaCtaId, LEA, an IADD3 per entry -- in every batch)
+template <int OFF>
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF));
+    return v;
+}
+
 template <bool FORM_B>
-__device__ __forceinline__ void fast_entries(const DevParams &P, const Self &self, const uint32_t *tslot,
-                                             const float4 *__restrict__ vel_s, const uint2 *__restrict__ vlp,
-                                             uint32_t nmax, uint2 q0, uint2 q1, float &ax_out, float &ay_out,
-                                             float &az_out) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int STRIDE = FORM_B ? NF_STRIDE_B : NF_STRIDE_A;
-    const float *const tx = reinterpret_cast<const float *>(smem_raw);
-    const float *const ty = tx + STRIDE, *const tz = tx + 2 * STRIDE;
-    const float4 *const tv = reinterpret_cast<const float4 *>(tx + 3 * NF_STRIDE_A);  // (form A)
+__device__ __forceinline__ void fast_entries(const DevParams &P, const Self &self, const uint32_t tile_s,
+                                             const uint32_t *tslot, const float4 *__restrict__ vel_s,
+                                             const uint2 *__restrict__ vlp, uint32_t nmax, uint2 q0, uint2 q1,
+                                             float &ax_out, float &ay_out, float &az_out) {
+    // tile_s: shared-space address of the tile, obtained AFTER the tile wait (every load below depends on it)
+    constexpr int STRIDE = (FORM_B ? NF_STRIDE_B : NF_STRIDE_A) * 4;  // bytes
+    constexpr int TV = 3 * NF_STRIDE_A * 4;                           // (form A) velocities
     const FastSelf F{self.p.x, self.p.y, self.p.z, self.vhat.x, self.vhat.y, self.vhat.z, self.v.x, self.v.y, self.v.z};
-    // velocity of an entry that contributes (form B: a padding entry has no slot to read)
-    auto vel_of = [&](uint32_t c, bool wanted) -> float4 {
-        const uint32_t t = c & 0xfffu;
-        if (!FORM_B) return tv[t];
-        return wanted ? __ldg(vel_s + (tslot[c >> 12] + t)) : make_float4(0, 0, 0, 0);
+    // velocity of an entry (form B: only of one that contributes -- a padding entry has no slot to read)
+    auto vel_of = [&](uint32_t c, uint32_t a4, bool wanted) -> float4 {  // a4: tile_s + 4 * offset
+        if (!FORM_B) return lds_f32x4<TV>(tile_s + 4u * (a4 - tile_s));
+        return wanted ? __ldg(vel_s + (tslot[c >> 12] + (c & 0xfffu))) : make_float4(0, 0, 0, 0);
     };
     float2 ax = f2s(0.0f), ay = ax, az = ax;
     const float cut = P.m2_cut, tol = P.fz_gc_tol;
     // one batch of four entries (an 8-byte word of the list)
     auto batch = [&](const uint2 q) {
-        const uint32_t c0 = q.x & 0xffffu, c1 = q.x >> 16, c2 = q.y & 0xffffu, c3 = q.y >> 16;
         // (rows past this lane's list hold the build's padding entry: a candidate 1e18 away)
-        const uint32_t t0 = c0 & 0xfffu, t1 = c1 & 0xfffu, t2 = c2 & 0xfffu, t3 = c3 & 0xfffu;
-        const FastPair2 fa = fast_gate2(P, F, f2(tx[t0], tx[t1]), f2(ty[t0], ty[t1]), f2(tz[t0], tz[t1]));
-        const FastPair2 fb = fast_gate2(P, F, f2(tx[t2], tx[t3]), f2(ty[t2], ty[t3]), f2(tz[t2], tz[t3]));
+        const uint32_t a0 = tile_s + ((q.x << 2) & 0x3ffcu), a1 = tile_s + ((q.x >> 14) & 0x3ffcu);
+        const uint32_t a2 = tile_s + ((q.y << 2) & 0x3ffcu), a3 = tile_s + ((q.y >> 14) & 0x3ffcu);
+        const FastPair2 fa = fast_gate2(P, F, f2(lds_f32<0>(a0), lds_f32<0>(a1)), f2(lds_f32<STRIDE>(a0), lds_f32<STRIDE>(a1)),
+                                        f2(lds_f32<2 * STRIDE>(a0), lds_f32<2 * STRIDE>(a1)));
+        const FastPair2 fb = fast_gate2(P, F, f2(lds_f32<0>(a2), lds_f32<0>(a3)), f2(lds_f32<STRIDE>(a2), lds_f32<STRIDE>(a3)),
+                                        f2(lds_f32<2 * STRIDE>(a2), lds_f32<2 * STRIDE>(a3)));
+        // in range <=> m2 < cut (NaN counts as in range and ends up `open`)
+        const bool i0 = !(fa.m2.x >= cut), i1 = !(fa.m2.y >= cut), i2 = !(fb.m2.x >= cut), i3 = !(fb.m2.y >= cut);
+        // batch-wide: a pair closer than 1e-6, or a cosine inside a guard band / NaN (of ANY entry, in
+        // range or not -- the exact evaluation below sorts that out): fmin / fmax drop a NaN operand
+        // only next to a number, and a NaN cosine comes from m2 = 0, which `tiny` sees
         const bool tiny = !(fminf(fminf(fa.m2.x, fa.m2.y), fminf(fb.m2.x, fb.m2.y)) >= 1e-12f);
-        const bool i0 = !(fa.m2.x >= cut) && !tiny, i1 = !(fa.m2.y >= cut) && !tiny;  // (NaN: in, then unsure)
-        const bool i2 = !(fb.m2.x >= cut) && !tiny, i3 = !(fb.m2.y >= cut) && !tiny;
-        const bool p0 = i0 && fa.gc.x > tol, p1 = i1 && fa.gc.y > tol, p2 = i2 && fb.gc.x > tol, p3 = i3 && fb.gc.y > tol;
-        const bool u0 = i0 && !(fabsf(fa.gc.x) > tol), u1 = i1 && !(fabsf(fa.gc.y) > tol);
-        const bool u2 = i2 && !(fabsf(fb.gc.x) > tol), u3 = i3 && !(fabsf(fb.gc.y) > tol);
-        if (p0 || p1) fast_force2(P, F, fa, p0, p1, vel_of(c0, p0), vel_of(c1, p1), ax, ay, az);
-        if (p2 || p3) fast_force2(P, F, fb, p2, p3, vel_of(c2, p2), vel_of(c3, p3), ax, ay, az);
-        if (tiny || u0 || u1 || u2 || u3) {
-            // guard band / degenerate pair (rare): the reference's own sequence decides and evaluates
-            // (which entries: the flags taken above, not a second evaluation of the cosine -- the
-            //  compiler may fuse the two differently, and an entry must go exactly one way)
-            const uint32_t open_mask = tiny ? 0xfu : (u0 ? 1u : 0u) | (u1 ? 2u : 0u) | (u2 ? 4u : 0u) | (u3 ? 8u : 0u);
+        const bool open = tiny || !(fminf(fminf(fabsf(fa.gc.x), fabsf(fa.gc.y)), fminf(fabsf(fb.gc.x), fabsf(fb.gc.y))) > tol);
+        if (!open) {
+            const bool p0 = i0 && fa.gc.x > tol, p1 = i1 && fa.gc.y > tol, p2 = i2 && fb.gc.x > tol, p3 = i3 && fb.gc.y > tol;
+            if (p0 || p1) fast_force2(P, F, fa, p0, p1, vel_of(q.x & 0xffffu, a0, p0), vel_of(q.x >> 16, a1, p1), ax, ay, az);
+            if (p2 || p3) fast_force2(P, F, fb, p2, p3, vel_of(q.y & 0xffffu, a2, p2), vel_of(q.y >> 16, a3, p3), ax, ay, az);
+        } else {
+            // rare: every in-range entry of the batch goes down the reference's own sequence, which
+            // decides (field of view) and evaluates
 #pragma unroll 1
             for (uint32_t u = 0; u < 4; ++u) {
-                if (!(open_mask >> u & 1u)) continue;
-                const uint32_t cu = u == 0 ? c0 : u == 1 ? c1 : u == 2 ? c2 : c3;
-                const uint32_t tu = cu & 0xfffu;
-                const float dx = fsub(tx[tu], self.p.x), dy = fsub(ty[tu], self.p.y), dz = fsub(tz[tu], self.p.z);
-                const float m2 = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));  // (the same bits as above)
+                const uint32_t cu = u == 0 ? (q.x & 0xffffu) : u == 1 ? (q.x >> 16) : u == 2 ? (q.y & 0xffffu) : (q.y >> 16);
+                const uint32_t au = tile_s + 4u * (cu & 0xfffu);
+                const float dx = fsub(lds_f32<0>(au), self.p.x), dy = fsub(lds_f32<STRIDE>(au), self.p.y),
+                            dz = fsub(lds_f32<2 * STRIDE>(au), self.p.z);
+                const float m2 = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
                 if (m2 >= cut) continue;
-                const float4 vj = vel_of(cu, true);
+                const float4 vj = vel_of(cu, au, true);
                 V3 contrib;
                 if (pair_inrange<false>(P, self, v3(dx, dy, dz), m2, v3(vj.x, vj.y, vj.z), 1.0f, P.cstar, contrib)) {
                     ax.x += contrib.x;
@@ -673,7 +654,7 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     const uint32_t tid = threadIdx.x;
     const uint32_t s = io.first + blockIdx.x * NL_BLOCK + tid;
     const bool active = s < io.last;
-    const NlPrologue pro = nl_prologue<TAP == TAP_STEP, true>(io, nl, tid, s, active);
+    const NlPrologue pro = nl_prologue<TAP == TAP_STEP>(io, nl, tid, s, active);
     const uint32_t no_lists = pro.no_lists, ub = pro.ub, ue = pro.ue;
     const float4 pi4 = pro.pi4, vi4 = pro.vi4;
     const uint32_t n_c = pro.n_c;
@@ -733,12 +714,13 @@ nl_fast_kernel(const DevParams P, const GridDesc g, const WalkIO io, const NlIO 
     const uint32_t nmax = __reduce_max_sync(0xffffffffu, n_c);
     const uint32_t total = S.toff[9];
     if (total > 0) mbar_wait(&S.bar, 0);
-    nl_warm_successor<true>(pro, io, nl, tid, true);
+    uint32_t tile_s;  // (volatile: stays behind the wait, and every tile load depends on it)
+    asm volatile("mov.u32 %0, %1;" : "=r"(tile_s) : "r"(smem_u32(smem_raw)) : "memory");
     float ax, ay, az;
     if (total > (uint32_t)NF_TILE)
-        fast_entries<true>(P, self, S.tslot, io.vel_s, pro.vlp, nmax, pro.q0, pro.q1, ax, ay, az);
+        fast_entries<true>(P, self, tile_s, S.tslot, io.vel_s, pro.vlp, nmax, pro.q0, pro.q1, ax, ay, az);
     else
-        fast_entries<false>(P, self, S.tslot, io.vel_s, pro.vlp, nmax, pro.q0, pro.q1, ax, ay, az);
+        fast_entries<false>(P, self, tile_s, S.tslot, io.vel_s, pro.vlp, nmax, pro.q0, pro.q1, ax, ay, az);
     if (!active) return;
     if (!work) ax = ay = az = 0.0f;  // (steering overrides, ghost record: the lists were walked for nothing)
     walk_finish<TAP, true>(P, s, pi4, vi4, self, v3(ax, ay, az), 0u, 0ull, io, status, tap);
@@ -755,32 +737,6 @@ size_t nl_cta_tab_elems(uint32_t rows) {
 }
 uint32_t nl_tile_cap(bool fast) { return fast ? NF_TILE : NL_TILE; }
 uint32_t nl_tile_cap_b(bool fast) { return fast ? NF_TILE_B : 0; }
-// CTAs of a list walk that are resident on the current device at once (0 if that cannot be told)
-uint32_t nl_walk_resident_ctas(bool fast) {
-    static uint32_t cached[2] = {~0u, ~0u};
-    uint32_t &c = cached[fast ? 1 : 0];
-    if (c == ~0u) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) {
-            if (fast) {
-                const int smem = (int)(sizeof(float) * NF_SMEM_FLOATS + sizeof(NlFastTail));
-                e = cudaFuncSetAttribute(nl_fast_kernel<TAP_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                if (e == cudaSuccess)
-                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nl_fast_kernel<TAP_STEP>, NL_BLOCK, smem);
-            } else {
-                const int smem = (int)sizeof(NlWalkSmem);
-                e = cudaFuncSetAttribute(nl_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nl_walk_kernel, NL_BLOCK, smem);
-            }
-        }
-        if (e != cudaSuccess) (void)cudaGetLastError();
-        c = e == cudaSuccess ? (uint32_t)(sms * per_sm) : 0u;
-    }
-    return c;
-}
-
 int launch_nl_build(cudaStream_t st, const GridDesc &g, const WalkIO &io, const NlIO &nl) {
     if (io.last <= io.first) return FP_OK;
     const uint32_t ctas = (io.last - io.first + NL_BLOCK - 1) / NL_BLOCK;
