@@ -124,7 +124,7 @@ static int with_gpu() {
         auto a = state::State<SpringyPoint>(dev).rk4_step(0.01f).euler_step(0.02f).as_vector();
         auto b = state::State<SpringyPointHost>(host).rk4_step(0.01f).euler_step(0.02f).as_vector();
         CHECK(a.size() == 10000 && std::memcmp(a.data(), b.data(), a.size() * 4) == 0);
-        CHECK(a[4] != 0.5f);
+        CHECK(a[14] != 0.5f);  // (element 1: force 0.3 on mass 1.01 moved its velocity; element 0 carries none)
     }
     {   // the demo's sim 1 (demos/flocking.rs:105-121) stepped headless two ways: must agree bit for bit
         std::vector<float> st;
