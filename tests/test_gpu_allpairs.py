@@ -273,3 +273,43 @@ def test_small_kernels_bit_exact_vs_oracle(orc, n):
     for _ in range(5):
         cur, _ = orc.step(c2, sc, cur)
     assert np.array_equal(bits(sim.read_state()), bits(cur))
+
+
+def test_small_flock_write_step_read_through_mapped_memory(orc):
+    """Demo-sized flocks: fp_flock_write_state leaves the rows in a pinned, device-mapped slot, the
+    single-CTA step kernel ingests them itself and writes the advanced rows to mapped memory for
+    fp_flock_read_state -- no copy, no conversion kernel.  Same bits as the oracle whichever way the
+    calls interleave: write -> step -> read loops, a write that no step follows, taps between a write
+    and a step, several steps per launch, a method change with rows still pending."""
+    c = orc.default_config()
+    st = synth.uniform_flock(110, 14.0, seed=61)
+    for method in (_lib.METHOD_SMALL, _lib.METHOD_AUTO):
+        sim, sc = make_pair(c, st, method, TABLES)
+        cur = st.copy()
+        for k in range(6):                       # the e2e loop of bench.py
+            sim.write_state(cur)
+            sim.step()
+            cur, _ = orc.step(c, sc, cur)
+            got = sim.read_state()
+            assert np.array_equal(bits(got), bits(cur)), (method, k)
+            assert np.array_equal(bits(sim.read_state()), bits(cur))      # a second read: same rows
+        other = synth.uniform_flock(110, 14.0, seed=62)
+        sim.write_state(other)                   # no step: the rows come back unchanged
+        assert np.array_equal(bits(sim.read_state()), bits(other))
+        sim.write_state(cur)
+        ref_acc, _, _ = orc.accel_rows(c, sc, cur)
+        assert np.array_equal(bits(sim.read_accel()), bits(ref_acc))      # a tap ingests pending rows
+        sim.step_many(3)
+        for _ in range(3):
+            cur, _ = orc.step(c, sc, cur)
+        assert np.array_equal(bits(sim.read_state()), bits(cur))
+        sim.step()                               # a step straight after a read: state still on the device
+        cur, _ = orc.step(c, sc, cur)
+        assert np.array_equal(bits(sim.read_state()), bits(cur))
+    # rows pending when the method changes: the all-pairs kernel must see them
+    sim, sc = make_pair(c, st, _lib.METHOD_SMALL, TABLES)
+    sim.write_state(other)
+    sim.set_method(_lib.METHOD_ALLPAIRS)
+    sim.step()
+    ref, _ = orc.step(c, sc, other)
+    assert np.array_equal(bits(sim.read_state()), bits(ref))
