@@ -370,6 +370,10 @@ class Simulation:
         check(self._lib.fp_flock_export_instances(self._h, C.c_void_p(dst_ptr), 1 if raw else 0))
 
     def read_accel(self, components: bool = False):
+        """ADDITION (debug tap): the acceleration the NEXT step would apply -- with the lead boids
+        where they stand now (``step()`` leaves the library holding the rows of the step before)."""
+        if self.lead_boids:
+            self._push_leads()
         acc = np.empty((self._n, 3), np.float32)
         comp = np.empty((self._n, 5, 3), np.float32) if components else None
         check(self._lib.fp_flock_read_accel(self._h, ptr(acc), ptr(comp)))
