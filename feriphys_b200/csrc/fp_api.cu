@@ -1062,8 +1062,9 @@ int fp_flock_get_method(fp_flock *f, int *method_in_use) {
 }
 
 int fp_flock_set_leads(fp_flock *f, uint32_t n_leads, const float *leads7) {
-    // (no settle: the steps in flight keep the rows they were enqueued with -- see fp_flock.h)
-    int rc = check(f, false);
+    // (no settle: the steps in flight keep the rows they were enqueued with -- see fp_flock.h;
+    //  the boid state is not touched: rows pending in a pinned slot / mapped output rows stay)
+    int rc = check(f, false, true);
     if (rc) return rc;
     if (n_leads && !leads7) { set_error("null leads"); return FP_ERR_INVALID; }
     constexpr uint32_t RING = fp_flock::LEAD_RING, STAGES = fp_flock::LEAD_STAGES;

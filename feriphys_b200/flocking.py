@@ -266,11 +266,11 @@ class Simulation:
         if self.lead_boids:
             self._push_leads()
         check(self._lib.fp_flock_step(self._h, 1))
+        dt = self.get_timestep()
         if self.lead_boids:
-            dt = Duration.from_secs_f32(self.config.dt)
             for lead in self.lead_boids:
                 lead.step(dt)
-        return self.get_timestep()
+        return dt
 
     def step_many(self, nsteps: int) -> Duration:
         """ADDITION: ``nsteps`` steps in one library call; the lead boids' rows are
