@@ -122,7 +122,11 @@ int fp_flock_set_lead_table(fp_flock *f, uint32_t steps, uint32_t n_leads, const
 int fp_flock_step(fp_flock *f, uint32_t nsteps);
 int fp_flock_sync(fp_flock *f);
 
-/* ADDITIONS (F4): state in caller index order, n x 6 floats. */
+/* ADDITIONS (F4): state in caller index order, n x 6 floats.  Neither call retains the caller's
+ * buffer.  Flocks up to 256 KB: write_state copies the rows into a pinned, device-mapped slot and
+ * returns without touching the device; on the single-CTA kernel (FP_METHOD_SMALL) the next step reads
+ * them from there and leaves the advanced rows in mapped memory for read_state -- a write / step /
+ * read round is one launch and one stream synchronisation. */
 int fp_flock_read_state(fp_flock *f, float *out_aos6);
 int fp_flock_write_state(fp_flock *f, const float *state_aos6);
 uint64_t fp_flock_len(const fp_flock *f);
