@@ -245,6 +245,28 @@ class OracleRunner:
             self.grid = None
 
 
+def literal_rows_rate(r, seconds):
+    """The reference's own algorithm on one thread: literal O(N) rows of the oracle (no grid).
+    -> {"value": boid-steps/s, "rows": m, "sample": ...}"""
+    C = r.C
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def go(m):
+        out = np.empty((m, 3), np.float32)
+        t0 = time.perf_counter()
+        r.orc.lib.orc_accel_rows(C.byref(r.cfg), C.byref(r.sc), r.n, P(r.state), 0, m, P(out), None, None, 1)
+        return time.perf_counter() - t0
+
+    m = 1
+    t = max(go(m), 1e-6)
+    if t < seconds / 4:
+        m = int(max(1, min(r.n, seconds / t)))
+        t = max(go(m), 1e-6)
+    return {"value": m / t, "unit": "boid-steps/s", "cores": 1, "rows": m,
+            "sample": f"accelerations of the first {m} of {r.n} boids, each against all {r.n} (the reference's "
+                      f"O(N^2) loop, single thread, as the reference runs it)"}
+
+
 def sample_text(r, m):
     how = "grid-accelerated oracle (bit-identical to the literal loops)" if r.grid is not None \
         else "literal O(N) rows"
@@ -700,6 +722,9 @@ def run_ours(args, w, rank, world, local_rank):
         tsec = r.rows(m)
         line["cpu_baseline"] = {"value": m / tsec, "unit": "boid-steps/s", "cores": threads, "kind": "port",
                                 "sample": sample_text(r, m)}
+        # beside it, what the reference itself does (flocking.rs:133-151): one thread, every other boid
+        # visited for every boid -- a few literal rows, ~2 s
+        line["cpu_baseline"]["literal_single_thread"] = literal_rows_rate(r, 2.0)
         r.close()
     else:
         line["cpu_baseline"] = None
